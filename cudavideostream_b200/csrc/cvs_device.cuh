@@ -1,0 +1,121 @@
+// cvs_device.cuh -- small device-side helpers shared by the sm_100a kernels of libcvs_b200.
+//
+// Byte-SIMD-in-a-register helpers (four BGR bytes per 32-bit lane), cache-hinted vector
+// loads/stores and the descriptor primitives of the cross-block payload-offset exchange.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cvs {
+
+// ------------------------------------------------------------------------------------------
+// 16-byte global accesses with streaming hints.  Frames are read once (evict-first / no L1
+// allocation); payload stores are streaming as well.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+// reference frame: re-read next frame, keep it in L2
+__device__ __forceinline__ uint4 ldg_keep(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_keep(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream(void *p, uint4 v)
+{
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_u32(void *p, uint32_t v)
+{
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u8(void *p, uint32_t v)
+{
+    asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// payload-offset descriptors: one 64-bit word per (frame, segment, block) = (epoch << 32) | count.
+// The count travels in the same word as the tag, so relaxed accesses are sufficient.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void desc_publish(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long desc_peek(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-byte compare on 4 packed bytes.
+//   changed <=> |cur - ref| > thr  (server/include/common.h:14 LR_THRESHOLDS; test.cu:565)
+// ad   = per-byte absolute difference
+// addc = per-byte constant, hi = false: (128 - (thr+1)) for thr <= 127
+//                           hi = true : (256 - (thr+1)) for 128 <= thr <= 254, 0 for thr = 255
+// returns 0x80 in every byte lane that changed.
+// ------------------------------------------------------------------------------------------
+template <bool HI>
+__device__ __forceinline__ uint32_t changed80(uint32_t ad, uint32_t addc)
+{
+    uint32_t low = (ad & 0x7f7f7f7fu) + addc; // no carry between byte lanes: 127 + 127 < 256
+    return (HI ? (low & ad) : (low | ad)) & 0x80808080u;
+}
+
+// 0x80 flags -> 0xFF byte masks (PRMT with the sign-replicate bit set in every selector nibble)
+__device__ __forceinline__ uint32_t spread80(uint32_t m80)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(m80));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
+
+// horizontal sum of the four byte lanes (each lane <= 63 so the sum fits)
+__device__ __forceinline__ uint32_t hsum4(uint32_t x) { return (x * 0x01010101u) >> 24; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// splitmix64 finaliser (the synthetic camera's counter-based generator; twin in synth.py)
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+} // namespace cvs

@@ -1,0 +1,183 @@
+/*
+ * cvs_b200.h -- C ABI of libcvs_b200.so: the B200-native (sm_100a) replacement for the per-pixel
+ * hot path of MatteoBattilana/CUDAVideoStream's server.
+ *
+ * The reference exposes this path as the C++ class diff::cuda::CUDACore
+ * (server/include/kernels.cuh:13-43; implementation server/src/kernels.cu:377-536).  Its four
+ * public members are re-implemented, with unchanged signatures, by include/cvs_cuda_core.hpp +
+ * cudavideostream_b200/csrc/cvs_shim.cpp, which are thin calls into the functions declared here.
+ * Every entry point below names the reference interface it replaces.  Plain pointers and sizes
+ * only; no CUDA, torch or OpenCV types appear in any signature (a cudaStream_t is passed as void*).
+ *
+ * Error convention: every function returns a cvs_status; cvs_last_error() gives a message for the
+ * calling thread.  (The reference prints and exit()s inside CUDA_CHECK, kernels.cu:11-22; the C++
+ * shim converts a non-zero status into exactly that behaviour.)
+ *
+ * Pixel layout everywhere: packed row-major BGR24 ("RGB24" in OpenCV byte order), no row padding,
+ * N = 3*width*height bytes per frame.
+ */
+#ifndef CVS_B200_H_
+#define CVS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVS_ABI_VERSION 1
+
+typedef enum cvs_status {
+    CVS_OK = 0,
+    CVS_ERR_INVALID = 1,   /* bad argument                                                    */
+    CVS_ERR_CUDA = 2,      /* a CUDA runtime call failed (message in cvs_last_error)          */
+    CVS_ERR_NOMEM = 3,
+    CVS_ERR_ALIGN = 4,     /* device pointer / stride not 16-byte aligned                     */
+    CVS_ERR_CAPACITY = 5,  /* payload_capacity too small for a frame of the sequence          */
+    CVS_ERR_NODEVICE = 6,  /* no sm_100 device: there is no CPU fallback                      */
+    CVS_ERR_INTERNAL = 7   /* device-side watchdog tripped (look-back did not resolve)        */
+} cvs_status;
+
+/* NOISE_VISUALIZER values of server/include/common.h:9-10, plus two extensions (6, 7) that expose
+ * the average-grayscale variants of server/src/server.cpp:96-135. */
+typedef enum cvs_mode {
+    CVS_MODE_NONE = 0,
+    CVS_MODE_HEAT_MAP = 1,          /* kernels.cu:243-270 / tests/heat_map_benchmark/cpu.cu        */
+    CVS_MODE_RED_BLACK = 2,         /* kernels.cu:273-281 on a zeroed frame (kernels.cu:513-515)   */
+    CVS_MODE_RED_OVERLAP = 3,       /* kernels.cu:517 on the previous reference frame              */
+    CVS_MODE_GRAY_WEIGHTED = 4,     /* kernels.cu:67-95 / tests/grayscale-weighted/cpu.cu:38-42    */
+    CVS_MODE_BINARIZE = 5,          /* kernels.cu:493-499: weighted gray, hist, two-max, binarize  */
+    CVS_MODE_GRAY_AVERAGE = 6,      /* server.cpp:96-101                                           */
+    CVS_MODE_BINARIZE_AVERAGE = 7   /* server.cpp:96-135 (the CPU branch, average gray)            */
+} cvs_mode;
+
+/* Runtime form of the compile-time switches in server/include/common.h:4-18 plus the constructor
+ * arguments of CUDACore (kernels.cuh:38).  Fill with cvs_config_default() first. */
+typedef struct cvs_config {
+    int width;                 /* frameSz.width                                               */
+    int height;                /* frameSz.height                                              */
+    int threshold;             /* LR_THRESHOLDS (common.h:14), default 20; changed <=> |df| > threshold */
+    int mode;                  /* cvs_mode                                                    */
+    int noise_filter;          /* NOISE_FILTER (common.h:5): 1 = K x K convolution before the diff */
+    int ksize;                 /* K (common.h:6): odd, 1..9                                   */
+    const float *kweights;     /* ksize*ksize weights, row major (CUDACore ctor `k`)          */
+    int device;                /* CUDA device ordinal (the reference hard-codes 0)            */
+    const uint8_t *base_frame; /* first reference frame, N bytes, host (sampleMatData)        */
+    const uint8_t *glyphs;     /* glyph atlas charsPx: nglyphs x (glyph_h x glyph_w x 3) bytes, or NULL */
+    int glyph_w, glyph_h;      /* charsSz                                                     */
+    const char *glyph_chars;   /* CHARS_STR (common.h:13): character of glyph i              */
+    int max_sequence;          /* largest nframes a cvs_run_sequence_device call will use (default 512) */
+} cvs_config;
+
+typedef struct cvs_stream_s *cvs_handle; /* one camera stream = one reference-frame state */
+
+const char *cvs_last_error(void);
+int cvs_abi_version(void);
+/* number of visible sm_100 devices (0 => nothing in this library can run) */
+int cvs_device_count(void);
+
+void cvs_config_default(cvs_config *cfg);
+
+/* replaces CUDACore::CUDACore (kernels.cu:377-428): allocates device state, uploads base frame */
+cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out);
+cvs_status cvs_destroy(cvs_handle h);
+/* re-seed the reference frame (the reference has no resync) */
+cvs_status cvs_reset(cvs_handle h, const uint8_t *base_frame);
+
+/* replaces CUDACore::alloc_arrays (kernels.cu:531-536): pinned host memory */
+cvs_status cvs_alloc_host(void **ptr, size_t bytes);
+cvs_status cvs_free_host(void *ptr);
+
+/* replaces CUDACore::exec_core (kernels.cu:430-525), synchronous.
+ *   frame : in  N-byte frame (pinned or pageable host memory)
+ *           out frame[0..*pos) = diff bytes (df & 0xFF), rest untouched   (kernels.cu:522)
+ *   show  : out N-byte visualisation frame when mode != 0 (may be NULL)   (showReadyNData)
+ *   text  : overlay string over glyph_chars, may be NULL/empty            (kernels.cu:466-476)
+ *   pos   : out number of changed bytes                                   (kernels.cu:507)
+ *   xs    : out xs[0..*pos) ascending byte indices, capacity N ints       (kernels.cu:523)
+ */
+cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text,
+                    unsigned int *pos, int *xs);
+
+/* Pipelined form of the same call: cvs_submit enqueues H2D + kernels + D2H on the stream's
+ * double-buffered slots and returns a ticket; cvs_wait blocks until that frame's outputs are on
+ * the host.  At most 2 tickets may be outstanding.  Host buffers must be pinned (cvs_alloc_host)
+ * for the copies to overlap. */
+cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text,
+                      unsigned int *pos, int *xs, uint64_t *ticket);
+cvs_status cvs_wait(cvs_handle h, uint64_t ticket);
+
+/* device times of the most recent completed cvs_exec / cvs_wait, microseconds (CUDA events):
+ * host-to-device copy, kernels, device-to-host copies -- reported separately, as the
+ * reference's report does (REPORT/report.tex:922-926). */
+cvs_status cvs_get_timing(cvs_handle h, float *h2d_us, float *kernel_us, float *d2h_us);
+
+/* copy the current reference frame (client-reconstructed image) to host memory, N bytes */
+cvs_status cvs_get_reference(cvs_handle h, uint8_t *out);
+/* device pointer of the reference frame (16-byte aligned, N bytes valid) */
+cvs_status cvs_reference_device(cvs_handle h, void **dptr);
+
+/* Device-resident sequence: the whole hot path over `nframes` consecutive frames that are already
+ * in device memory, one persistent launch, asynchronous on `cuda_stream` (a cudaStream_t, NULL =
+ * default stream).  This is the path bench.py times for `value` (inputs resident in HBM).
+ *   d_frames        frame t at d_frames + t*frame_stride; base and stride 16-byte aligned,
+ *                   stride >= N rounded up to 16
+ *   d_pos           [nframes] changed-byte count per frame
+ *   d_xs, d_diff    frame t's payload at d_xs + t*payload_capacity (ints) and
+ *                   d_diff + t*payload_capacity (bytes); payload_capacity entries per frame.
+ *                   Entries beyond the capacity are dropped and the call's completion status
+ *                   (cvs_sequence_status) reports CVS_ERR_CAPACITY; d_pos still holds the true count.
+ *   d_show          NULL, or frame t's visualisation at d_show + t*show_stride (mode != 0)
+ * Noise filter and text overlay are applied per frame exactly as in cvs_exec (text fixed for the call).
+ */
+cvs_status cvs_run_sequence_device(cvs_handle h, const uint8_t *d_frames, size_t frame_stride,
+                                   int nframes, unsigned int *d_pos, int *d_xs, uint8_t *d_diff,
+                                   size_t payload_capacity, uint8_t *d_show, size_t show_stride,
+                                   const char *text, void *cuda_stream);
+/* after the stream has been synchronised: status word the last sequence launch left behind */
+cvs_status cvs_sequence_status(cvs_handle h);
+/* how many kernels of this library the handle has launched so far (bench.py's gpu_launches) */
+uint64_t cvs_launch_count(cvs_handle h);
+
+/* Stand-alone filters on device buffers (config 4 of BASELINE.json and the micro-benchmarks of
+ * tests/heat_map_benchmark, tests/heat_map_red_benchmark, tests/grayscale-*, tests/binarization,
+ * tests/noise_filter_benchmark).  All pointers are device pointers, 16-byte aligned; asynchronous
+ * on `cuda_stream`.  `device` selects the GPU.                                                  */
+cvs_status cvs_heat_map_device(const uint8_t *d_prev, const uint8_t *d_cur, uint8_t *d_out,
+                               int width, int height, void *cuda_stream);
+cvs_status cvs_red_map_device(const uint8_t *d_prev, const uint8_t *d_cur, uint8_t *d_out,
+                              int width, int height, int threshold, void *cuda_stream);
+/* weighted != 0: 0.114 B + 0.587 G + 0.299 R (double, truncated); else (B+G+R)/3.
+ * channels = 1 (P bytes out) or 3 (value replicated, N bytes out). */
+cvs_status cvs_grayscale_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height,
+                                int weighted, int channels, void *cuda_stream);
+/* gray (weighted or average) -> 256-bin histogram -> two-max threshold clamped to
+ * [clamp_lo, clamp_hi] -> 3-channel 0/255 image.  d_hist_thr: 257 ints of scratch/out
+ * (histogram[256], threshold). */
+cvs_status cvs_binarize_device(const uint8_t *d_frame, uint8_t *d_out, int *d_hist_thr, int width,
+                               int height, int weighted, int clamp_lo, int clamp_hi,
+                               void *cuda_stream);
+/* K x K zero-padded convolution, fp32 FMA accumulation in row-major tap order, truncation */
+cvs_status cvs_noise_filter_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height,
+                                   int ksize, const float *h_weights, void *cuda_stream);
+/* client side of the wire format (client/opencv.cpp:64-66): frame[xs[i]] += diff[i] */
+cvs_status cvs_client_apply_device(uint8_t *d_frame, const int *d_xs, const uint8_t *d_diff,
+                                   const unsigned int *d_pos, size_t capacity, void *cuda_stream);
+
+/* Synthetic camera used by bench.py and the parity tests: counter-based
+ * splitmix64 so that the numpy twin in cudavideostream_b200/synth.py produces identical bytes.
+ *   cvs_synth_base_device   : base frame (diagonal gradient + noise)
+ *   cvs_synth_next_device   : frame t from frame t-1; each byte changes by +-U[21,80] with
+ *                             probability density_ppm/1e6, otherwise drifts by U[-3,3]
+ */
+cvs_status cvs_synth_base_device(uint8_t *d_out, int width, int height, uint64_t seed,
+                                 void *cuda_stream);
+cvs_status cvs_synth_next_device(const uint8_t *d_prev, uint8_t *d_out, int width, int height,
+                                 uint64_t seed, uint32_t frame_index, uint32_t density_ppm,
+                                 void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVS_B200_H_ */

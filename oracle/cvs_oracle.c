@@ -1,0 +1,478 @@
+/*
+ * cvs_oracle.c -- CPU ORACLE for the CUDAVideoStream hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is a plain-C restatement of the reference's own CPU loops (MatteoBattilana/
+ * CUDAVideoStream).  It is the checker the CUDA path is compared against; nothing in the
+ * product (cudavideostream_b200/) links, imports or calls it.  Only tests/, the
+ * __graft_entry__.smoke() check and bench.py's cpu_baseline / --impl reference legs use it.
+ *
+ * Parity pinning: the reference has no automated tests; the known answers it does hold are
+ * checked in tests/test_oracle_kat.py:
+ *   K1  f1.jpg/f2.jpg changed-byte count 369,350            (REPORT/report.tex:2594)
+ *   K2  3x3 mean filter on the report's matrices A and B     (REPORT/report.tex:2351-2378)
+ *   K4  histogram example                                    (REPORT/report.tex:3141-3187)
+ *   K6  red byte of a changed byte index: i + (2 - i%3)      (REPORT/report.tex:2234)
+ * The ordered (xs, diff) payload has no golden vector anywhere in the reference, so it is
+ * pinned by this restatement of tests/cuda_streaming/test.cu:560-576 plus the client
+ * round-trip property (client/opencv.cpp:64-66).
+ *
+ * Each function cites the reference file:line it follows (paths relative to the reference
+ * root).  Floating point is kept in the reference's types and evaluation order; build with
+ * -O2 -ffp-contract=off so that no contraction is introduced except where fmaf() is written
+ * explicitly (orc_noise_filter, see its comment).
+ *
+ * Pixel layout: packed, row-major, 3 bytes per pixel in OpenCV order B,G,R, no row padding.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ---------------------------------------------------------------------------------------
+ * A1  thresholded difference + ordered compaction + negative feedback
+ *     tests/cuda_streaming/test.cu:560-576 (twin: server/src/server.cpp:82-94, commented)
+ *
+ *   frame     in : current frame (N bytes).  out: frame[0..pos) = diff bytes (df & 0xFF), the
+ *                  rest of the buffer keeps the input frame (the reference writes the payload
+ *                  over the head of the frame buffer while it is still reading its tail).
+ *   previous  in : reference frame (what the client has reconstructed).  out: new reference
+ *                  = changed ? current : previous  (pvs[i] -= df  <=>  pvs[i] = previous[i]).
+ *   xs        out: ascending byte indices of the changed bytes.
+ *   returns pos.
+ * ------------------------------------------------------------------------------------- */
+ORC_API unsigned orc_diff_compact(uint8_t *frame, uint8_t *previous, int *xs, int total, int thr)
+{
+    uint8_t *pvs = (uint8_t *)malloc((size_t)total > 0 ? (size_t)total : 1);
+    memcpy(pvs, frame, (size_t)total);                /* Mat pvs = pframe->clone()        :560 */
+    unsigned pos = 0;                                 /* pready->h_pos = 0                :562 */
+    for (int i = 0; i < total; i++) {                 /*                                  :563 */
+        int df = frame[i] - previous[i];              /*                                  :564 */
+        if (df < -thr || df > thr) {                  /* LR_THRESHOLDS                    :565 */
+            frame[pos] = (uint8_t)df;                 /*                                  :566 */
+            xs[pos] = i;                              /*                                  :567 */
+            pos++;                                    /*                                  :568 */
+        } else {
+            pvs[i] -= df;                             /*                                  :570 */
+        }
+    }
+    memcpy(previous, pvs, (size_t)total);             /* previous = pvs                   :574 */
+    free(pvs);
+    return pos;
+}
+
+/* client side: frame2.data[xs[i]] += buffer[i] (uint8 wrap add)   client/opencv.cpp:64-66 */
+ORC_API void orc_client_apply(uint8_t *frame, const int *xs, const uint8_t *diff, unsigned pos)
+{
+    for (unsigned i = 0; i < pos; i++)
+        frame[xs[i]] += diff[i];
+}
+
+/* tests/noise_filter_benchmark/v2.cu:106-114 getCountDifference (threshold literal 20 there) */
+ORC_API int orc_count_difference(const uint8_t *orig, const uint8_t *mod, int total, int thr)
+{
+    int count = 0;
+    for (int i = 0; i < total; i++)
+        if (abs(orig[i] - mod[i]) > thr)
+            count++;
+    return count;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A3  grayscale average
+ * ------------------------------------------------------------------------------------- */
+/* server/src/server.cpp:96-101 : in place, value replicated to the 3 channels */
+ORC_API void orc_gray_avg3(uint8_t *data, int total)
+{
+    for (int i = 0; i + 2 < total; i = i + 3) {
+        int sum = data[i] + data[i + 1] + data[i + 2];
+        data[i] = sum / 3;
+        data[i + 1] = sum / 3;
+        data[i + 2] = sum / 3;
+    }
+}
+
+/* tests/grayscale-average/cpu.cu:38-43 : one channel out */
+ORC_API void orc_gray_avg1(const uint8_t *frame, uint8_t *out, int width, int height)
+{
+    for (int row = 0; row < height; row++)
+        for (int col = 0; col < width; col++) {
+            const uint8_t *p = frame + 3 * ((size_t)row * width + col);
+            int sum = p[0] + p[1] + p[2];
+            out[(size_t)row * width + col] = sum / 3;
+        }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A4  grayscale weighted    tests/grayscale-weighted/cpu.cu:38-42, tests/binarization/cpu.cu:43-47
+ *     uchar = 0.114*B + 0.587*G + 0.299*R : double products, left-to-right double adds,
+ *     conversion to uchar truncates.
+ * ------------------------------------------------------------------------------------- */
+static inline uint8_t orc_wgray(const uint8_t *p)
+{
+    double v = 0.114 * p[0] + 0.587 * p[1] + 0.299 * p[2];
+    return (uint8_t)v;
+}
+
+ORC_API void orc_gray_weighted1(const uint8_t *frame, uint8_t *out, int width, int height)
+{
+    for (int row = 0; row < height; row++)
+        for (int col = 0; col < width; col++)
+            out[(size_t)row * width + col] = orc_wgray(frame + 3 * ((size_t)row * width + col));
+}
+
+/* 3-channel replicated form, the shape server/src/kernels.cu:67-95 produces for modes 4/5 */
+ORC_API void orc_gray_weighted3(const uint8_t *frame, uint8_t *out, int total)
+{
+    for (int i = 0; i + 2 < total; i += 3) {
+        uint8_t g = orc_wgray(frame + i);
+        out[i] = g;
+        out[i + 1] = g;
+        out[i + 2] = g;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A5  histogram    server/src/server.cpp:103-106 (one sample per pixel of the 3-ch gray image)
+ * ------------------------------------------------------------------------------------- */
+ORC_API void orc_histogram3(const uint8_t *gray3, int total, int *histogram /*[256]*/)
+{
+    for (int i = 0; i < 256; i++)
+        histogram[i] = 0;
+    for (int i = 0; i < total; i = i + 3)
+        histogram[gray3[i]]++;
+}
+
+/* tests/binarization/cpu.cu:57-65 : one-channel image */
+ORC_API void orc_histogram1(const uint8_t *gray1, int npix, int *histogram /*[256]*/)
+{
+    for (int i = 0; i < 256; i++)
+        histogram[i] = 0;
+    for (int i = 0; i < npix; i++)
+        histogram[gray1[i]]++;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A7  "two max" threshold    server/src/server.cpp:108-127 (= tests/binarization/cpu.cu:72-87)
+ *     The loop is restated literally, including the quirk that sec_max is set to the NEW max
+ *     so the else-if can never fire; index_sec_max ends up as the previous running arg-max
+ *     (possibly -1).  clamp_lo/clamp_hi: server.cpp uses [50,200]; the stand-alone test uses
+ *     only "<20 -> 20" (pass clamp_hi = 255 there).
+ * ------------------------------------------------------------------------------------- */
+ORC_API int orc_threshold_twomax(const int *histogram, int clamp_lo, int clamp_hi)
+{
+    int max = -1, sec_max = -1;
+    int index_max = -1, index_sec_max = -1;
+    for (int i = 0; i < 256; i++) {
+        if (histogram[i] >= max) {
+            index_sec_max = index_max;
+            index_max = i;
+            max = histogram[i];
+            sec_max = max;
+        } else if (histogram[i] > sec_max && histogram[i] < max) {
+            sec_max = histogram[i];
+            index_sec_max = i;
+        }
+    }
+    int threshold = (index_max + index_sec_max) / 2;
+    if (threshold < clamp_lo)
+        threshold = clamp_lo;
+    if (threshold > clamp_hi)
+        threshold = clamp_hi;
+    return threshold;
+}
+
+/* A6  binarize   server/src/server.cpp:129-135 */
+ORC_API void orc_binarize(uint8_t *data, int total, int threshold)
+{
+    for (int i = 0; i < total; i++) {
+        if (data[i] > threshold)
+            data[i] = 255;
+        else
+            data[i] = 0;
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A8  heat map   tests/heat_map_benchmark/cpu.cu:19-27 (getHeatPixel), :54-66 (loop)
+ * ------------------------------------------------------------------------------------- */
+ORC_API void orc_heat_pixel(int diff, int *r, int *g, int *b)
+{
+    float diff1 = diff / (255.0 * 2.0);                                     /* :21 */
+    *r = (int)fmin(fmax(sin(M_PI * diff1 - M_PI / 2.0) * 255.0, 0.0), 255.0); /* :22 */
+    *g = (int)fmin(fmax(sin(M_PI * diff1) * 255.0, 0.0), 255.0);             /* :23 */
+    *b = (int)fmin(fmax(sin(M_PI * diff1 + M_PI / 2.0) * 255.0, 0.0), 255.0); /* :24 */
+}
+
+ORC_API void orc_heat_map(const uint8_t *image1 /*previous*/, const uint8_t *image2 /*current*/,
+                          uint8_t *out, int width, int height)
+{
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            size_t o = 3 * ((size_t)y * width + x);
+            const uint8_t *a = image1 + o, *b = image2 + o;
+            int r, g, bl;
+            orc_heat_pixel(abs(a[0] - b[0]) + abs(a[1] - b[1]) + abs(a[2] - b[2]), &r, &g, &bl);
+            out[o + 0] = (uint8_t)bl;
+            out[o + 1] = (uint8_t)g;
+            out[o + 2] = (uint8_t)r;
+        }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A9  heat-map-red / noise visualizer   tests/heat_map_red_benchmark/cpu.cu:38-55
+ * ------------------------------------------------------------------------------------- */
+ORC_API void orc_red_map(const uint8_t *image1, const uint8_t *image2, uint8_t *out,
+                         int width, int height, int thr)
+{
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            size_t o = 3 * ((size_t)y * width + x);
+            const uint8_t *a = image1 + o, *b = image2 + o;
+            if (abs(a[0] - b[0]) > thr || abs(a[1] - b[1]) > thr || abs(a[2] - b[2]) > thr) {
+                out[o + 0] = 0;
+                out[o + 1] = 0;
+                out[o + 2] = 255;
+            } else {
+                out[o + 0] = 0;
+                out[o + 1] = 0;
+                out[o + 2] = 0;
+            }
+        }
+}
+
+/* server/src/kernels.cu:273-281 red_black_map_overlap, with every one of the pos entries
+ * applied (the reference's launch drops the last pos % 1024 entries, a defect not restated):
+ * out[xs + (2 - xs % 3)] = 255 for every changed byte index (K6, REPORT/report.tex:2234). */
+ORC_API void orc_red_overlap_from_xs(uint8_t *out, const int *xs, unsigned pos)
+{
+    for (unsigned i = 0; i < pos; i++)
+        out[xs[i] + (2 - xs[i] % 3)] = 255;
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A10 noise filter weights
+ * ------------------------------------------------------------------------------------- */
+/* server/src/server.cpp:20-36 computeGaussianKernel (K is a macro there; here a parameter) */
+ORC_API void orc_gaussian_kernel(float *k, int K, float sigma)
+{
+    float sum = 0;
+    for (int i = 0; i < K; i++) {
+        for (int j = 0; j < K; j++) {
+            float x = i - (K - 1) / 2.0;
+            float y = j - (K - 1) / 2.0;
+            k[i * K + j] = (1.0 / (2.0 * M_PI * sigma * sigma)) * exp(-((x * x + y * y) / (2.0 * sigma * sigma)));
+            sum += k[i * K + j];
+        }
+    }
+    for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++)
+            k[i * K + j] /= sum;
+}
+
+/* tests/noise_filter_benchmark/v2.cu:116-125 computeMeanKernel */
+ORC_API void orc_mean_kernel(float *k, int K)
+{
+    for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++)
+            k[i * K + j] = 1.0 / (K * K);
+}
+
+/* A10 noise filter   loop structure of server/src/kernels.cu:119-134 (= v2.cu:57-72):
+ *   float acc = 0; for i<K for j<K: acc += k[i*K+j] * pix(y+i-K/2, x+j-K/2); out = (u8)acc
+ * with zero padding outside the image for ALL three channels (the reference zeroes channel
+ * +1 twice and leaves channel +2 of the halo uninitialised, kernels.cu:114 -- a defect, not
+ * restated).  nvcc contracts "acc += k*p" into one FFMA, so the pinned behaviour is
+ * fmaf(k, pix, acc) in row-major tap order; this is what reproduces the report's known
+ * answer K2 (A centre 96.99999 -> 96; without contraction it is 97).  */
+ORC_API void orc_noise_filter(const uint8_t *image, uint8_t *out, int width, int height,
+                              int K, const float *k)
+{
+    for (int row = 0; row < height; row++)
+        for (int col = 0; col < width; col++)
+            for (int ch = 0; ch < 3; ch++) {
+                float acc = 0.0f;
+                for (int i = 0; i < K; i++)
+                    for (int j = 0; j < K; j++) {
+                        int r = row + i - K / 2, c = col + j - K / 2;
+                        float pix = 0.0f;
+                        if (r >= 0 && r < height && c >= 0 && c < width)
+                            pix = (float)image[3 * ((size_t)r * width + c) + ch];
+                        acc = fmaf(k[i * K + j], pix, acc);
+                    }
+                out[3 * ((size_t)row * width + col) + ch] = (uint8_t)acc;
+            }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * text overlay   server/src/kernels.cu:337-348 kernel_char (the byte-exact blit; host loop
+ * :466-476).  Glyph i of the atlas is a (gh x gw) BGR image; character j of the text goes to
+ * rows [0,gh), byte columns [j*gw*3, (j+1)*gw*3).  A character that is not in `chars` leaves
+ * the frame untouched (the reference reads an uninitialised index there, kernels.cu:467-473).
+ * Characters that would cross the right edge of the frame are dropped.
+ * ------------------------------------------------------------------------------------- */
+ORC_API void orc_text_overlay(uint8_t *frame, int width, int height, const uint8_t *glyphs,
+                              int gw, int gh, const char *chars, const char *text)
+{
+    int full_area = 3 * gw * gh;
+    int matrix_width = 3 * gw, curr_width = 3 * width;
+    int nchars = (int)strlen(chars);
+    int offset = 0;
+    for (int j = 0; text[j]; j++, offset += gw * 3) {
+        int idx = -1;
+        for (int i = 0; i < nchars; i++)
+            if (chars[i] == text[j]) {
+                idx = i;
+                break;
+            }
+        if (idx < 0 || offset + matrix_width > curr_width || gh > height)
+            continue;
+        const uint8_t *matrix = glyphs + (size_t)idx * full_area;
+        for (int i = 0; i < full_area; i++) {
+            int x = offset + i % matrix_width;
+            int y = i / matrix_width;
+            frame[(size_t)y * curr_width + x] = matrix[i];
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------
+ * A11 per-frame orchestration   server/src/kernels.cu:430-525 (CUDACore::exec_core), with
+ * every step computed by the CPU loops above.
+ *
+ * mode = NOISE_VISUALIZER (server/include/common.h:10): 0 none, 1 heat map, 2 red-black,
+ * 3 red-black overlap, 4 weighted gray, 5 binarization (weighted gray -> histogram ->
+ * two-max clamp [50,200] -> binarize).  mode 6 (ours) = average gray, mode 7 (ours) =
+ * binarization on the average gray exactly as the CPU branch server.cpp:96-135.
+ * ------------------------------------------------------------------------------------- */
+typedef struct orc_state {
+    int width, height, total, thr, mode, noise_filter, K;
+    float k[81];
+    uint8_t *reference; /* d_previous after the swap: what the client holds */
+    uint8_t *cur;       /* d_current */
+    const uint8_t *glyphs;
+    int gw, gh;
+    char chars[64];
+} orc_state;
+
+ORC_API orc_state *orc_create(int width, int height, int thr, int mode, int noise_filter, int K,
+                              const float *k, const uint8_t *base_frame, const uint8_t *glyphs,
+                              int gw, int gh, const char *chars)
+{
+    orc_state *s = (orc_state *)calloc(1, sizeof *s);
+    s->width = width; s->height = height; s->total = 3 * width * height;
+    s->thr = thr; s->mode = mode; s->noise_filter = noise_filter; s->K = K;
+    if (k) memcpy(s->k, k, sizeof(float) * K * K);
+    s->reference = (uint8_t *)malloc(s->total ? s->total : 1);
+    s->cur = (uint8_t *)malloc(s->total ? s->total : 1);
+    memcpy(s->reference, base_frame, s->total);          /* kernels.cu:406 */
+    s->glyphs = glyphs; s->gw = gw; s->gh = gh;
+    if (chars) strncpy(s->chars, chars, sizeof s->chars - 1);
+    return s;
+}
+
+ORC_API void orc_destroy(orc_state *s)
+{
+    if (!s) return;
+    free(s->reference); free(s->cur); free(s);
+}
+
+ORC_API const uint8_t *orc_reference(orc_state *s) { return s->reference; }
+
+ORC_API void orc_exec_core(orc_state *s, uint8_t *frame, uint8_t *show, const char *text,
+                           unsigned *h_pos, int *h_xs)
+{
+    int total = s->total;
+    /* kernels.cu:451-461: swap, then H2D (optionally through the noise filter) */
+    if (s->noise_filter)
+        orc_noise_filter(frame, s->cur, s->width, s->height, s->K, s->k);
+    else
+        memcpy(s->cur, frame, total);
+    /* kernels.cu:466-476 */
+    if (text && text[0] && s->glyphs)
+        orc_text_overlay(s->cur, s->width, s->height, s->glyphs, s->gw, s->gh, s->chars, text);
+    /* kernels.cu:478-502 */
+    if (show) {
+        if (s->mode == 1) {
+            orc_heat_map(s->reference, s->cur, show, s->width, s->height);
+        } else if (s->mode == 4) {
+            orc_gray_weighted3(s->cur, show, total);
+        } else if (s->mode == 5 || s->mode == 7) {
+            int hist[256];
+            if (s->mode == 5) orc_gray_weighted3(s->cur, show, total);
+            else { memcpy(show, s->cur, total); orc_gray_avg3(show, total); }
+            orc_histogram3(show, total, hist);
+            orc_binarize(show, total, orc_threshold_twomax(hist, 50, 200));
+        } else if (s->mode == 6) {
+            memcpy(show, s->cur, total); orc_gray_avg3(show, total);
+        } else if (s->mode == 3) {
+            memcpy(show, s->reference, total);            /* d_previous before kernel2 */
+        } else if (s->mode == 2) {
+            memset(show, 0, total);                       /* kernels.cu:513 */
+        }
+    }
+    /* kernels.cu:505 kernel2 == A1; payload goes to d_diff, then D2H over the frame head :522 */
+    uint8_t *tmp = (uint8_t *)malloc(total ? total : 1);
+    memcpy(tmp, s->cur, total);
+    unsigned pos = orc_diff_compact(tmp, s->reference, h_xs, total, s->thr);
+    memcpy(frame, tmp, pos);
+    free(tmp);
+    *h_pos = pos;
+    /* kernels.cu:511-520 */
+    if (show && (s->mode == 2 || s->mode == 3))
+        orc_red_overlap_from_xs(show, h_xs, pos);
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Timing helper for bench.py's cpu_baseline / --impl reference legs: nthreads independent
+ * camera streams, each running A1 frame after frame over its own copy of a frame ring
+ * (the reference's compute is single threaded per stream, server.cpp:70-146; independent
+ * streams are the only parallelism the path offers).  Returns seconds of wall time.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t *frames; int nframes_ring; int total; int thr; int iters; const uint8_t *base;
+    unsigned long long sum_pos;
+} orc_bench_arg;
+
+static void *orc_bench_thread(void *p)
+{
+    orc_bench_arg *a = (orc_bench_arg *)p;
+    uint8_t *work = (uint8_t *)malloc(a->total);
+    uint8_t *ref = (uint8_t *)malloc(a->total);
+    int *xs = (int *)malloc(sizeof(int) * (size_t)a->total);
+    memcpy(ref, a->base, a->total);
+    unsigned long long sum = 0;
+    for (int it = 0; it < a->iters; it++) {
+        memcpy(work, a->frames + (size_t)(it % a->nframes_ring) * a->total, a->total); /* "capture" */
+        sum += orc_diff_compact(work, ref, xs, a->total, a->thr);
+    }
+    a->sum_pos = sum;
+    free(work); free(ref); free(xs);
+    return NULL;
+}
+
+ORC_API double orc_bench_diff_compact(const uint8_t *frames, int nframes_ring, int total, int thr,
+                                      const uint8_t *base, int iters_per_thread, int nthreads,
+                                      unsigned long long *sum_pos_out)
+{
+    pthread_t th[256];
+    orc_bench_arg args[256];
+    if (nthreads > 256) nthreads = 256;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < nthreads; i++) {
+        args[i] = (orc_bench_arg){frames, nframes_ring, total, thr, iters_per_thread, base, 0};
+        pthread_create(&th[i], NULL, orc_bench_thread, &args[i]);
+    }
+    unsigned long long sum = 0;
+    for (int i = 0; i < nthreads; i++) {
+        pthread_join(th[i], NULL);
+        sum += args[i].sum_pos;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (sum_pos_out) *sum_pos_out = sum;
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
