@@ -1,0 +1,857 @@
+// cvs_api.cu -- host side of libcvs_b200.so: the C ABI declared in include/cvs_b200.h.
+//
+// Replaces the host orchestration of diff::cuda::CUDACore (server/src/kernels.cu:377-536).  There is
+// no CPU fallback anywhere in this file: without an sm_100 device every entry point that would
+// compute returns CVS_ERR_NODEVICE.
+#include "../../include/cvs_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "cvs_filter_kernels.cuh"
+#include "cvs_stream_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+cvs_status fail(cvs_status st, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return st;
+}
+
+#define CU_TRY(expr)                                                                                                   \
+    do {                                                                                                               \
+        cudaError_t e_ = (expr);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(CVS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+    } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool device_is_sm100(int dev)
+{
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    return major == 10;
+}
+
+// threshold constant for changed80<HI>
+void threshold_consts(int thr, bool &hi, uint32_t &addc)
+{
+    if (thr < -1) thr = -1;   // everything changes
+    if (thr > 255) thr = 255; // nothing changes
+    hi = thr >= 128;
+    uint32_t a = hi ? (uint32_t)(255 - thr) : (uint32_t)(127 - thr);
+    addc = a * 0x01010101u;
+}
+
+// heat-map colour table: the reference's getHeatPixel evaluated for every possible d
+// (tests/heat_map_benchmark/cpu.cu:19-27); entry = B | G<<8 | R<<16
+void build_heat_lut(uint32_t *lut)
+{
+    for (int d = 0; d < 766; d++) {
+        float diff1 = d / (255.0 * 2.0);
+        int r = (int)fmin(fmax(sin(M_PI * diff1 - M_PI / 2.0) * 255.0, 0.0), 255.0);
+        int g = (int)fmin(fmax(sin(M_PI * diff1) * 255.0, 0.0), 255.0);
+        int b = (int)fmin(fmax(sin(M_PI * diff1 + M_PI / 2.0) * 255.0, 0.0), 255.0);
+        lut[d] = (uint32_t)(b & 255) | ((uint32_t)(g & 255) << 8) | ((uint32_t)(r & 255) << 16);
+    }
+    lut[766] = lut[767] = 0;
+}
+
+// per-device constant tables for the stand-alone filter entry points
+std::mutex g_lut_mutex;
+uint32_t *g_dev_lut[64] = {nullptr};
+
+cvs_status device_heat_lut(uint32_t **out)
+{
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(CVS_ERR_INVALID, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_lut_mutex);
+    if (!g_dev_lut[dev]) {
+        uint32_t host[768];
+        build_heat_lut(host);
+        uint32_t *d = nullptr;
+        CU_TRY(cudaMalloc(&d, sizeof host));
+        CU_TRY(cudaMemcpy(d, host, sizeof host, cudaMemcpyHostToDevice));
+        g_dev_lut[dev] = d;
+    }
+    *out = g_dev_lut[dev];
+    return CVS_OK;
+}
+
+int grid_for(size_t items, int block, int sms)
+{
+    size_t blocks = (items + block - 1) / block;
+    size_t cap = (size_t)sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+struct Slot {
+    uint8_t *d_in = nullptr;   // raw frame as uploaded
+    int *d_xs = nullptr;
+    uint8_t *d_diff = nullptr;
+    unsigned int *d_pos = nullptr;
+    uint8_t *d_show = nullptr;
+    unsigned int *h_pos = nullptr; // pinned
+    cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_pos = nullptr,
+                ev_p0 = nullptr, ev_done = nullptr;
+    bool busy = false;
+    uint64_t ticket = 0;
+    uint8_t *u_frame = nullptr;
+    int *u_xs = nullptr;
+    unsigned int *u_pos = nullptr;
+};
+
+typedef void (*StreamKernel)(const cvs::StreamParams);
+
+template <int MODE>
+StreamKernel pick_hr(bool hi, bool refreg)
+{
+    if (hi) return refreg ? cvs::k_stream<MODE, true, true> : cvs::k_stream<MODE, true, false>;
+    return refreg ? cvs::k_stream<MODE, false, true> : cvs::k_stream<MODE, false, false>;
+}
+StreamKernel pick_kernel(int mode, bool hi, bool refreg)
+{
+    switch (mode) {
+    case 1: return pick_hr<1>(hi, refreg);
+    case 2: return pick_hr<2>(hi, refreg);
+    case 3: return pick_hr<3>(hi, refreg);
+    case 4: return pick_hr<4>(hi, refreg);
+    case 5: return pick_hr<5>(hi, refreg);
+    case 6: return pick_hr<6>(hi, refreg);
+    case 7: return pick_hr<7>(hi, refreg);
+    default: return pick_hr<0>(hi, refreg);
+    }
+}
+
+} // namespace
+
+struct cvs_stream_s {
+    int width = 0, height = 0, threshold = 20, mode = 0, noise_filter = 0, ksize = 3, device = 0;
+    int max_sequence = 512;
+    uint32_t N = 0, N16 = 0, ngroups = 0, npix = 0;
+    size_t Npad = 0, P16 = 0;
+    bool hi = false;
+    uint32_t addc = 0;
+    cvs::ConvWeights weights;
+    int sms = 0;
+    // glyph atlas
+    uint8_t *d_glyphs = nullptr;
+    int glyph_w = 0, glyph_h = 0;
+    std::string glyph_chars;
+    // device state
+    uint8_t *d_ref = nullptr;
+    uint32_t *d_lut = nullptr;
+    unsigned int *d_status = nullptr;
+    unsigned int *h_status = nullptr; // pinned
+    unsigned long long *d_desc = nullptr;
+    size_t desc_words = 0;
+    uint32_t epoch = 0;
+    // scratch that grows with the longest sequence seen
+    uint8_t *d_work = nullptr;   // filtered / overlaid frames
+    size_t work_frames = 0;
+    uint8_t *d_gray1 = nullptr;  // binarise: 1 B per pixel per frame
+    unsigned int *d_hist = nullptr;
+    int *d_thr = nullptr;
+    size_t bin_frames = 0;
+    // geometry of the persistent launch (per kernel variant)
+    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    Slot slot[2];
+    uint64_t next_ticket = 1;
+    uint64_t launches = 0;
+    float t_h2d = 0, t_kernel = 0, t_d2h = 0;
+    cvs_status seq_status = CVS_OK;
+};
+
+namespace {
+
+cvs_status ensure_desc(cvs_handle h, size_t words)
+{
+    if (h->desc_words >= words) return CVS_OK;
+    if (h->d_desc) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(h->d_desc));
+        h->d_desc = nullptr;
+        h->desc_words = 0;
+    }
+    CU_TRY(cudaMalloc(&h->d_desc, words * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(h->d_desc, 0, words * sizeof(unsigned long long)));
+    h->desc_words = words;
+    return CVS_OK;
+}
+
+cvs_status ensure_work(cvs_handle h, size_t frames)
+{
+    if (h->work_frames >= frames) return CVS_OK;
+    if (h->d_work) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(h->d_work));
+        h->d_work = nullptr;
+        h->work_frames = 0;
+    }
+    CU_TRY(cudaMalloc(&h->d_work, frames * h->Npad + 64));
+    CU_TRY(cudaMemset(h->d_work, 0, frames * h->Npad + 64));
+    h->work_frames = frames;
+    return CVS_OK;
+}
+
+cvs_status ensure_bin(cvs_handle h, size_t frames)
+{
+    if (h->bin_frames >= frames) return CVS_OK;
+    if (h->d_gray1) {
+        CU_TRY(cudaDeviceSynchronize());
+        CU_TRY(cudaFree(h->d_gray1));
+        CU_TRY(cudaFree(h->d_hist));
+        CU_TRY(cudaFree(h->d_thr));
+        h->d_gray1 = nullptr;
+        h->bin_frames = 0;
+    }
+    CU_TRY(cudaMalloc(&h->d_gray1, frames * h->P16 + 64));
+    CU_TRY(cudaMalloc(&h->d_hist, frames * 256 * sizeof(unsigned int)));
+    CU_TRY(cudaMalloc(&h->d_thr, frames * sizeof(int)));
+    h->bin_frames = frames;
+    return CVS_OK;
+}
+
+cvs_status launch_conv(const uint8_t *in, uint8_t *out, int width, int height, size_t in_stride, size_t out_stride,
+                       int nframes, int K, const cvs::ConvWeights &w, cudaStream_t st)
+{
+    const int rowbytes = 3 * width;
+    const bool fast = (rowbytes % 4 == 0) && (in_stride % 4 == 0) && (out_stride % 4 == 0) &&
+                      ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0) && (K == 1 || K == 3 || K == 5);
+    if (fast) {
+        dim3 block(256), grid((rowbytes / 4 + 255) / 256, height, nframes);
+        switch (K) {
+        case 1: cvs::k_conv_rows4<1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
+        case 3: cvs::k_conv_rows4<3><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
+        default: cvs::k_conv_rows4<5><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
+        }
+    } else {
+        dim3 block(256), grid((rowbytes + 255) / 256, height, nframes);
+        cvs::k_conv_bytes<<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, K, w);
+    }
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+// One pass of the whole hot path over nframes device-resident frames (A11, kernels.cu:455-520).
+cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int nframes, unsigned int *d_pos, int *d_xs,
+                      uint8_t *d_diff, size_t cap, uint8_t *d_show, size_t show_stride, const char *text,
+                      cudaStream_t st)
+{
+    if (nframes <= 0) return CVS_OK;
+    const uint8_t *frames = d_frames;
+    size_t fstride = stride;
+
+    // ---- text overlay glyph indices (kernels.cu:466-473); characters outside the atlas are skipped
+    cvs::OverlayText txt;
+    txt.n = 0;
+    if (text && text[0] && h->d_glyphs) {
+        int n = (int)strlen(text);
+        if (n > (int)sizeof txt.idx) n = (int)sizeof txt.idx;
+        for (int j = 0; j < n; j++) {
+            size_t at = h->glyph_chars.find(text[j]);
+            txt.idx[j] = (at == std::string::npos || at > 126) ? (signed char)-1 : (signed char)at;
+        }
+        txt.n = n;
+    }
+
+    // ---- pre-pass: noise filter and overlay write a private copy of the frames
+    if (h->noise_filter || txt.n) {
+        cvs_status s = ensure_work(h, (size_t)nframes);
+        if (s) return s;
+        if (h->noise_filter) {
+            s = launch_conv(d_frames, h->d_work, h->width, h->height, stride, h->Npad, nframes, h->ksize, h->weights, st);
+            if (s) return s;
+            h->launches++;
+        } else {
+            CU_TRY(cudaMemcpy2DAsync(h->d_work, h->Npad, d_frames, stride, h->N, nframes, cudaMemcpyDeviceToDevice, st));
+        }
+        if (txt.n && h->glyph_h <= h->height) {
+            const int area = 3 * h->glyph_w * h->glyph_h;
+            dim3 grid((area + 255) / 256, txt.n, nframes);
+            cvs::k_overlay<<<grid, 256, 0, st>>>(h->d_work, h->Npad, h->width, h->d_glyphs, h->glyph_w, h->glyph_h, txt);
+            CU_TRY(cudaGetLastError());
+            h->launches++;
+        }
+        frames = h->d_work;
+        fstride = h->Npad;
+    }
+
+    const int mode = h->mode;
+    const bool binarize = (mode == 5 || mode == 7) && d_show;
+    const int kmode = d_show ? mode : 0; // without a display buffer only the payload is produced
+    if (binarize) {
+        cvs_status s = ensure_bin(h, (size_t)nframes);
+        if (s) return s;
+        CU_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)nframes * 256 * sizeof(unsigned int), st));
+    }
+    if (kmode == 2) {
+        // nothing: the fused kernel writes every byte of the red-black frame
+    }
+
+    // ---- geometry of the persistent launch
+    int G = 2 * h->sms;
+    if (G > cvs::kThreads) G = cvs::kThreads;
+    if ((uint32_t)G > h->ngroups) G = (int)h->ngroups;
+    uint32_t nseg = (uint32_t)((h->ngroups + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+    uint32_t gps = (uint32_t)((h->ngroups + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+    const bool refreg = nseg == 1;
+    StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cvs::SmemLayout::total));
+    int occ = 0;
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, cvs::SmemLayout::total));
+    if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
+    if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
+        G = occ * h->sms;
+        nseg = (uint32_t)((h->ngroups + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+        gps = (uint32_t)((h->ngroups + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+        if ((nseg == 1) != refreg) return fail(CVS_ERR_INTERNAL, "occupancy changed the segment count");
+    }
+
+    int done = 0;
+    while (done < nframes) {
+        int chunk = nframes - done;
+        if (chunk > h->max_sequence) chunk = h->max_sequence;
+        cvs_status s = ensure_desc(h, (size_t)chunk * nseg * (G + 1));
+        if (s) return s;
+        h->epoch++;
+        if (h->epoch == 0) { // tag wrapped: stale descriptors could alias
+            CU_TRY(cudaMemsetAsync(h->d_desc, 0, h->desc_words * sizeof(unsigned long long), st));
+            h->epoch = 1;
+        }
+        cvs::StreamParams p;
+        p.frames = frames + (size_t)done * fstride;
+        p.frame_stride = fstride;
+        p.nframes = chunk;
+        p.ref = h->d_ref;
+        p.nbytes = h->N;
+        p.nbytes16 = h->N16;
+        p.ngroups = h->ngroups;
+        p.nseg = nseg;
+        p.gps = gps;
+        p.pos = d_pos + done;
+        p.xs = d_xs + (size_t)done * cap;
+        p.diff = d_diff + (size_t)done * cap;
+        p.cap = cap;
+        p.show = d_show ? d_show + (size_t)done * show_stride : nullptr;
+        p.show_stride = show_stride;
+        p.gray1 = binarize ? h->d_gray1 + (size_t)done * h->P16 : nullptr;
+        p.gray_stride = h->P16;
+        p.hist = binarize ? h->d_hist + (size_t)done * 256 : nullptr;
+        p.heat_lut = h->d_lut;
+        p.desc = h->d_desc;
+        p.epoch = h->epoch;
+        p.addc = h->addc;
+        p.status = h->d_status;
+        void *args[] = {&p};
+        CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(cvs::kThreads), args,
+                                           (size_t)cvs::SmemLayout::total, st));
+        h->launches++;
+        done += chunk;
+    }
+
+    if (binarize) {
+        cvs::k_threshold<<<(nframes + 63) / 64, 64, 0, st>>>(h->d_hist, h->d_thr, nframes, 50, 200);
+        CU_TRY(cudaGetLastError());
+        dim3 grid(grid_for((h->npix + 15) / 16, 256, h->sms), nframes);
+        cvs::k_binarize_expand<<<grid, 256, 0, st>>>(h->d_gray1, h->P16, d_show, show_stride, h->d_thr, h->npix);
+        CU_TRY(cudaGetLastError());
+        h->launches += 2;
+    }
+    return CVS_OK;
+}
+
+cvs_status check_handle(cvs_handle h)
+{
+    if (!h) return fail(CVS_ERR_INVALID, "null handle");
+    CU_TRY(cudaSetDevice(h->device));
+    return CVS_OK;
+}
+
+cvs_status status_word(cvs_handle h)
+{
+    unsigned int w = *h->h_status;
+    if (w & cvs::kStatusWatchdog) return fail(CVS_ERR_INTERNAL, "device watchdog tripped (status 0x%x)", w);
+    if (w & cvs::kStatusCapacity) return fail(CVS_ERR_CAPACITY, "payload capacity exceeded");
+    return CVS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *cvs_last_error(void) { return g_err; }
+int cvs_abi_version(void) { return CVS_ABI_VERSION; }
+
+int cvs_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int ok = 0;
+    for (int i = 0; i < n; i++)
+        if (device_is_sm100(i)) ok++;
+    return ok;
+}
+
+void cvs_config_default(cvs_config *cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->width = 1920;  // server/src/threads.cpp:37-38
+    cfg->height = 1080;
+    cfg->threshold = 20; // LR_THRESHOLDS, common.h:14
+    cfg->mode = 0;
+    cfg->noise_filter = 0;
+    cfg->ksize = 3; // K, common.h:6
+    cfg->max_sequence = 512;
+}
+
+cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
+{
+    if (!cfg || !out) return fail(CVS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->width <= 0 || cfg->height <= 0) return fail(CVS_ERR_INVALID, "bad frame size %dx%d", cfg->width, cfg->height);
+    if ((uint64_t)cfg->width * cfg->height * 3 > 0x7fffffffull - 64)
+        return fail(CVS_ERR_INVALID, "frame too large for 32-bit byte indices");
+    if (cfg->mode < 0 || cfg->mode > 7) return fail(CVS_ERR_INVALID, "bad mode %d", cfg->mode);
+    if (cfg->noise_filter && (cfg->ksize < 1 || cfg->ksize > 9 || !(cfg->ksize & 1) || !cfg->kweights))
+        return fail(CVS_ERR_INVALID, "noise filter needs an odd ksize in 1..9 and weights");
+    if (!cfg->base_frame) return fail(CVS_ERR_INVALID, "base_frame is required");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return fail(CVS_ERR_NODEVICE, "CUDA device %d not available (there is no CPU fallback)", cfg->device);
+    }
+    if (!device_is_sm100(cfg->device))
+        return fail(CVS_ERR_NODEVICE, "device %d is not sm_100 (there is no CPU fallback)", cfg->device);
+    CU_TRY(cudaSetDevice(cfg->device));
+
+    cvs_handle h = new cvs_stream_s();
+    h->width = cfg->width;
+    h->height = cfg->height;
+    h->threshold = cfg->threshold;
+    h->mode = cfg->mode;
+    h->noise_filter = cfg->noise_filter ? 1 : 0;
+    h->ksize = cfg->ksize;
+    h->device = cfg->device;
+    h->max_sequence = cfg->max_sequence > 0 ? cfg->max_sequence : 512;
+    h->npix = (uint32_t)cfg->width * (uint32_t)cfg->height;
+    h->N = 3u * h->npix;
+    h->N16 = (uint32_t)round_up(h->N, 16);
+    h->ngroups = (h->N + cvs::kGroupBytes - 1) / cvs::kGroupBytes;
+    h->Npad = (size_t)h->ngroups * cvs::kGroupBytes;
+    h->P16 = round_up(h->npix, 16);
+    threshold_consts(cfg->threshold, h->hi, h->addc);
+    memset(&h->weights, 0, sizeof h->weights);
+    if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
+    CU_TRY(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device));
+
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CU_TRY(cudaMalloc(&h->d_ref, h->Npad + 64));
+    CU_TRY(cudaMemset(h->d_ref, 0, h->Npad + 64));
+    CU_TRY(cudaMemcpy(h->d_ref, cfg->base_frame, h->N, cudaMemcpyHostToDevice)); // kernels.cu:406
+    {
+        uint32_t lut[768];
+        build_heat_lut(lut);
+        CU_TRY(cudaMalloc(&h->d_lut, sizeof lut));
+        CU_TRY(cudaMemcpy(h->d_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
+    }
+    CU_TRY(cudaMalloc(&h->d_status, sizeof(unsigned int)));
+    CU_TRY(cudaMemset(h->d_status, 0, sizeof(unsigned int)));
+    CU_TRY(cudaHostAlloc(&h->h_status, sizeof(unsigned int), cudaHostAllocDefault));
+    *h->h_status = 0;
+    if (cfg->glyphs && cfg->glyph_w > 0 && cfg->glyph_h > 0 && cfg->glyph_chars) {
+        h->glyph_chars = cfg->glyph_chars;
+        h->glyph_w = cfg->glyph_w;
+        h->glyph_h = cfg->glyph_h;
+        size_t bytes = h->glyph_chars.size() * 3 * (size_t)cfg->glyph_w * cfg->glyph_h;
+        CU_TRY(cudaMalloc(&h->d_glyphs, bytes + 16));
+        CU_TRY(cudaMemcpy(h->d_glyphs, cfg->glyphs, bytes, cudaMemcpyHostToDevice));
+    }
+    const size_t cap = round_up(h->N, 4);
+    for (Slot &s : h->slot) {
+        CU_TRY(cudaMalloc(&s.d_in, h->Npad + 64));
+        CU_TRY(cudaMemset(s.d_in, 0, h->Npad + 64));
+        CU_TRY(cudaMalloc(&s.d_xs, cap * sizeof(int)));
+        CU_TRY(cudaMalloc(&s.d_diff, cap));
+        CU_TRY(cudaMalloc(&s.d_pos, sizeof(unsigned int)));
+        if (h->mode) CU_TRY(cudaMalloc(&s.d_show, h->Npad + 64));
+        CU_TRY(cudaHostAlloc(&s.h_pos, sizeof(unsigned int), cudaHostAllocDefault));
+        cudaEvent_t *evs[] = {&s.ev_h2d0, &s.ev_h2d1, &s.ev_k0, &s.ev_k1, &s.ev_pos, &s.ev_p0, &s.ev_done};
+        for (cudaEvent_t *e : evs) CU_TRY(cudaEventCreate(e));
+    }
+    CU_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return CVS_OK;
+}
+
+cvs_status cvs_destroy(cvs_handle h)
+{
+    if (!h) return CVS_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (Slot &s : h->slot) {
+        cudaFree(s.d_in); cudaFree(s.d_xs); cudaFree(s.d_diff); cudaFree(s.d_pos); cudaFree(s.d_show);
+        cudaFreeHost(s.h_pos);
+        cudaEvent_t evs[] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.ev_p0, s.ev_done};
+        for (cudaEvent_t e : evs)
+            if (e) cudaEventDestroy(e);
+    }
+    cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
+    cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
+    cudaFree(h->d_glyphs);
+    if (h->s_comp) cudaStreamDestroy(h->s_comp);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    delete h;
+    return CVS_OK;
+}
+
+cvs_status cvs_reset(cvs_handle h, const uint8_t *base_frame)
+{
+    cvs_status s = check_handle(h);
+    if (s) return s;
+    if (!base_frame) return fail(CVS_ERR_INVALID, "null base frame");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(h->d_ref, base_frame, h->N, cudaMemcpyHostToDevice));
+    return CVS_OK;
+}
+
+cvs_status cvs_alloc_host(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(CVS_ERR_INVALID, "null argument");
+    *ptr = nullptr;
+    if (cvs_device_count() == 0) return fail(CVS_ERR_NODEVICE, "no sm_100 device (there is no CPU fallback)");
+    CU_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable));
+    return CVS_OK;
+}
+
+cvs_status cvs_free_host(void *ptr)
+{
+    if (!ptr) return CVS_OK;
+    CU_TRY(cudaFreeHost(ptr));
+    return CVS_OK;
+}
+
+cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
+                         unsigned int *pos, int *xs, uint64_t *ticket)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    if (!frame || !diff_out || !pos || !xs || !ticket) return fail(CVS_ERR_INVALID, "null argument");
+    Slot &s = h->slot[h->next_ticket & 1];
+    if (s.busy) return fail(CVS_ERR_INVALID, "two tickets are already outstanding; cvs_wait the oldest first");
+
+    // H2D (kernels.cu:461)
+    CU_TRY(cudaEventRecord(s.ev_h2d0, h->s_h2d));
+    CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
+    CU_TRY(cudaEventRecord(s.ev_h2d1, h->s_h2d));
+    // kernels
+    CU_TRY(cudaStreamWaitEvent(h->s_comp, s.ev_h2d1, 0));
+    CU_TRY(cudaEventRecord(s.ev_k0, h->s_comp));
+    const size_t cap = round_up(h->N, 4);
+    uint8_t *dshow = (h->mode && show) ? s.d_show : nullptr;
+    st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp);
+    if (st) return st;
+    CU_TRY(cudaEventRecord(s.ev_k1, h->s_comp));
+    // D2H of the count (kernels.cu:507) and of the display frame
+    CU_TRY(cudaStreamWaitEvent(h->s_d2h, s.ev_k1, 0));
+    CU_TRY(cudaEventRecord(s.ev_p0, h->s_d2h));
+    CU_TRY(cudaMemcpyAsync(s.h_pos, s.d_pos, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (dshow) CU_TRY(cudaMemcpyAsync(show, dshow, h->N, cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(cudaEventRecord(s.ev_pos, h->s_d2h));
+    s.busy = true;
+    s.ticket = h->next_ticket++;
+    s.u_frame = diff_out;
+    s.u_xs = xs;
+    s.u_pos = pos;
+    *ticket = s.ticket;
+    return CVS_OK;
+}
+
+cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text, unsigned int *pos, int *xs,
+                      uint64_t *ticket)
+{
+    return cvs_submit_io(h, frame, frame, show, text, pos, xs, ticket);
+}
+
+cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    Slot &s = h->slot[ticket & 1];
+    if (!s.busy || s.ticket != ticket) return fail(CVS_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
+    s.busy = false;
+    CU_TRY(cudaEventSynchronize(s.ev_pos));
+    st = status_word(h);
+    if (st == CVS_ERR_INTERNAL) return st;
+    const unsigned int n = *s.h_pos;
+    // payload (kernels.cu:522-523): diff bytes over the head of the frame buffer, then the indices
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(s.u_frame, s.d_diff, n, cudaMemcpyDeviceToHost, h->s_d2h));
+        CU_TRY(cudaMemcpyAsync(s.u_xs, s.d_xs, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    CU_TRY(cudaEventRecord(s.ev_done, h->s_d2h));
+    CU_TRY(cudaEventSynchronize(s.ev_done));
+    *s.u_pos = n;
+    float a = 0, b = 0, c = 0, d = 0;
+    CU_TRY(cudaEventElapsedTime(&a, s.ev_h2d0, s.ev_h2d1));
+    CU_TRY(cudaEventElapsedTime(&b, s.ev_k0, s.ev_k1));
+    CU_TRY(cudaEventElapsedTime(&c, s.ev_p0, s.ev_pos));
+    CU_TRY(cudaEventElapsedTime(&d, s.ev_pos, s.ev_done));
+    h->t_h2d = a * 1000.f;
+    h->t_kernel = b * 1000.f;
+    h->t_d2h = (c + d) * 1000.f;
+    return CVS_OK;
+}
+
+cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text, unsigned int *pos, int *xs)
+{
+    uint64_t ticket = 0;
+    cvs_status st = cvs_submit(h, frame, show, text, pos, xs, &ticket);
+    if (st) return st;
+    return cvs_wait(h, ticket);
+}
+
+cvs_status cvs_get_timing(cvs_handle h, float *h2d_us, float *kernel_us, float *d2h_us)
+{
+    if (!h) return fail(CVS_ERR_INVALID, "null handle");
+    if (h2d_us) *h2d_us = h->t_h2d;
+    if (kernel_us) *kernel_us = h->t_kernel;
+    if (d2h_us) *d2h_us = h->t_d2h;
+    return CVS_OK;
+}
+
+cvs_status cvs_get_reference(cvs_handle h, uint8_t *out)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    if (!out) return fail(CVS_ERR_INVALID, "null argument");
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(out, h->d_ref, h->N, cudaMemcpyDeviceToHost));
+    return CVS_OK;
+}
+
+cvs_status cvs_reference_device(cvs_handle h, void **dptr)
+{
+    if (!h || !dptr) return fail(CVS_ERR_INVALID, "null argument");
+    *dptr = h->d_ref;
+    return CVS_OK;
+}
+
+cvs_status cvs_run_sequence_device(cvs_handle h, const uint8_t *d_frames, size_t frame_stride, int nframes,
+                                   unsigned int *d_pos, int *d_xs, uint8_t *d_diff, size_t payload_capacity,
+                                   uint8_t *d_show, size_t show_stride, const char *text, void *cuda_stream)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    if (nframes < 0 || !d_frames || !d_pos || !d_xs || !d_diff) return fail(CVS_ERR_INVALID, "null argument");
+    if (((uintptr_t)d_frames & 15) || (frame_stride & 15) || ((uintptr_t)d_xs & 15) || ((uintptr_t)d_diff & 15) ||
+        (d_show && (((uintptr_t)d_show & 15) || (show_stride & 15))))
+        return fail(CVS_ERR_ALIGN, "device pointers and strides must be 16-byte aligned");
+    if (frame_stride < h->N16) return fail(CVS_ERR_INVALID, "frame_stride %zu < %u", frame_stride, h->N16);
+    if (d_show && show_stride < h->N) return fail(CVS_ERR_INVALID, "show_stride too small");
+    if (payload_capacity == 0 || (payload_capacity & 3))
+        return fail(CVS_ERR_INVALID, "payload_capacity must be a positive multiple of 4");
+    h->seq_status = CVS_OK;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    st = run_frames(h, d_frames, frame_stride, nframes, d_pos, d_xs, d_diff, payload_capacity, d_show, show_stride, text, s);
+    if (st) return st;
+    CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    return CVS_OK;
+}
+
+cvs_status cvs_sequence_status(cvs_handle h)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    st = status_word(h);
+    if (*h->h_status) { // sticky bits are cleared once reported
+        CU_TRY(cudaMemset(h->d_status, 0, sizeof(unsigned int)));
+        *h->h_status = 0;
+    }
+    return st;
+}
+
+uint64_t cvs_launch_count(cvs_handle h) { return h ? h->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone filters on device buffers (current device)
+// ---------------------------------------------------------------------------------------------
+static cvs_status filter_common(int &sms)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || !device_is_sm100(dev)) {
+        cudaGetLastError();
+        return fail(CVS_ERR_NODEVICE, "no sm_100 device (there is no CPU fallback)");
+    }
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return CVS_OK;
+}
+
+cvs_status cvs_heat_map_device(const uint8_t *d_prev, const uint8_t *d_cur, uint8_t *d_out, int width, int height,
+                               void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_prev || !d_cur || !d_out || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_prev | (uintptr_t)d_cur | (uintptr_t)d_out) & 15) return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    uint32_t *lut = nullptr;
+    st = device_heat_lut(&lut);
+    if (st) return st;
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height;
+    cvs::k_filter<0, false><<<grid_for((n + 47) / 48, 256, sms), 256, 0, (cudaStream_t)cuda_stream>>>(d_prev, d_cur, d_out, n, 0, lut, nullptr);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_red_map_device(const uint8_t *d_prev, const uint8_t *d_cur, uint8_t *d_out, int width, int height,
+                              int threshold, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_prev || !d_cur || !d_out || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_prev | (uintptr_t)d_cur | (uintptr_t)d_out) & 15) return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    bool hi;
+    uint32_t addc;
+    threshold_consts(threshold, hi, addc);
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height;
+    const int grid = grid_for((n + 47) / 48, 256, sms);
+    if (hi) cvs::k_filter<1, true><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_prev, d_cur, d_out, n, addc, nullptr, nullptr);
+    else cvs::k_filter<1, false><<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(d_prev, d_cur, d_out, n, addc, nullptr, nullptr);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+static cvs_status gray_launch(const uint8_t *d_frame, uint8_t *d_out, uint32_t n, int weighted, int channels,
+                              unsigned int *d_hist, int sms, cudaStream_t s)
+{
+    const int grid = grid_for((n + 47) / 48, 256, sms);
+    if (channels == 3) {
+        if (weighted) cvs::k_filter<3, false><<<grid, 256, 0, s>>>(nullptr, d_frame, d_out, n, 0, nullptr, nullptr);
+        else cvs::k_filter<2, false><<<grid, 256, 0, s>>>(nullptr, d_frame, d_out, n, 0, nullptr, nullptr);
+    } else {
+        if (weighted) cvs::k_filter<5, false><<<grid, 256, 0, s>>>(nullptr, d_frame, d_out, n, 0, nullptr, d_hist);
+        else cvs::k_filter<4, false><<<grid, 256, 0, s>>>(nullptr, d_frame, d_out, n, 0, nullptr, d_hist);
+    }
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_grayscale_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height, int weighted,
+                                int channels, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_frame || !d_out || width <= 0 || height <= 0 || (channels != 1 && channels != 3))
+        return fail(CVS_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_frame | (uintptr_t)d_out) & 15) return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    return gray_launch(d_frame, d_out, 3u * (uint32_t)width * (uint32_t)height, weighted, channels, nullptr, sms,
+                       (cudaStream_t)cuda_stream);
+}
+
+cvs_status cvs_binarize_device(const uint8_t *d_frame, uint8_t *d_out, uint8_t *d_gray, int *d_hist_thr, int width,
+                               int height, int weighted, int clamp_lo, int clamp_hi, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_frame || !d_out || !d_gray || !d_hist_thr || width <= 0 || height <= 0)
+        return fail(CVS_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_frame | (uintptr_t)d_out | (uintptr_t)d_gray) & 15)
+        return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const uint32_t npix = (uint32_t)width * (uint32_t)height;
+    CU_TRY(cudaMemsetAsync(d_hist_thr, 0, 257 * sizeof(int), s));
+    st = gray_launch(d_frame, d_gray, 3u * npix, weighted, 1, (unsigned int *)d_hist_thr, sms, s);
+    if (st) return st;
+    cvs::k_threshold<<<1, 32, 0, s>>>((const unsigned int *)d_hist_thr, d_hist_thr + 256, 1, clamp_lo, clamp_hi);
+    CU_TRY(cudaGetLastError());
+    cvs::k_binarize_expand<<<dim3(grid_for((npix + 15) / 16, 256, sms), 1), 256, 0, s>>>(d_gray, 0, d_out, 0,
+                                                                                        d_hist_thr + 256, npix);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_noise_filter_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height, int ksize,
+                                   const float *h_weights, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_frame || !d_out || !h_weights || width <= 0 || height <= 0 || ksize < 1 || ksize > 9 || !(ksize & 1))
+        return fail(CVS_ERR_INVALID, "bad argument");
+    if (d_frame == d_out) return fail(CVS_ERR_INVALID, "the noise filter is not in-place");
+    cvs::ConvWeights w;
+    memset(&w, 0, sizeof w);
+    memcpy(w.k, h_weights, sizeof(float) * ksize * ksize);
+    const size_t n = (size_t)3 * width * height;
+    return launch_conv(d_frame, d_out, width, height, n, n, 1, ksize, w, (cudaStream_t)cuda_stream);
+}
+
+cvs_status cvs_client_apply_device(uint8_t *d_frame, const int *d_xs, const uint8_t *d_diff, const unsigned int *d_pos,
+                                   size_t capacity, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_frame || !d_xs || !d_diff || !d_pos) return fail(CVS_ERR_INVALID, "null argument");
+    cvs::k_client_apply<<<sms * 4, 256, 0, (cudaStream_t)cuda_stream>>>(d_frame, d_xs, d_diff, d_pos, capacity);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_synth_base_device(uint8_t *d_out, int width, int height, uint64_t seed, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_out || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height;
+    cvs::k_synth_base<<<grid_for(n, 256, sms), 256, 0, (cudaStream_t)cuda_stream>>>(d_out, n, width, height, seed);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_synth_next_device(const uint8_t *d_prev, uint8_t *d_out, int width, int height, uint64_t seed,
+                                 uint32_t frame_index, uint32_t density_ppm, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_prev || !d_out || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height;
+    const uint64_t key = cvs::splitmix64(seed ^ ((uint64_t)(frame_index + 1) * 0xD6E8FEB86659FD93ull));
+    cvs::k_synth_next<<<grid_for(n, 256, sms), 256, 0, (cudaStream_t)cuda_stream>>>(d_prev, d_out, n, key, density_ppm);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+} // extern "C"

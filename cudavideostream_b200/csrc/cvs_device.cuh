@@ -1,7 +1,8 @@
 // cvs_device.cuh -- small device-side helpers shared by the sm_100a kernels of libcvs_b200.
 //
 // Byte-SIMD-in-a-register helpers (four BGR bytes per 32-bit lane), cache-hinted vector
-// loads/stores and the descriptor primitives of the cross-block payload-offset exchange.
+// loads/stores, the mbarrier / bulk-copy (TMA) primitives of the frame ingest ring and the
+// descriptor primitives of the cross-block payload-offset exchange.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,9 +10,9 @@
 namespace cvs {
 
 // ------------------------------------------------------------------------------------------
-// 16-byte global accesses with streaming hints.  Frames are read once (evict-first / no L1
-// allocation); payload stores are streaming as well.
+// 16-byte global accesses with cache hints.
 // ------------------------------------------------------------------------------------------
+// frames that are read exactly once
 __device__ __forceinline__ uint4 ldg_stream(const void *p)
 {
     uint4 v;
@@ -20,21 +21,31 @@ __device__ __forceinline__ uint4 ldg_stream(const void *p)
                  : "l"(p));
     return v;
 }
-// reference frame: re-read next frame, keep it in L2
-__device__ __forceinline__ uint4 ldg_keep(const void *p)
+// reference frame: re-read by the next frame, keep it in L2 (evict-last policy through a cache hint;
+// the plain .L2::evict_last qualifier only exists for 256-bit accesses).  NOT .nc: the same thread
+// rewrites the line.
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint4 ldg_keep(const void *p, uint64_t pol)
 {
     uint4 v;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol)
+                 : "memory");
     return v;
 }
-__device__ __forceinline__ void stg_keep(void *p, uint4 v)
+__device__ __forceinline__ void stg_keep(void *p, uint4 v, uint64_t pol)
 {
-    asm volatile("st.global.L1::no_allocate.L2::evict_last.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
-                 "r"(v.y), "r"(v.z), "r"(v.w)
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
                  : "memory");
 }
+// outputs nobody on the device reads again (payload, display frames)
 __device__ __forceinline__ void stg_stream(void *p, uint4 v)
 {
     asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
@@ -47,6 +58,74 @@ __device__ __forceinline__ void stg_stream_u32(void *p, uint32_t v)
 __device__ __forceinline__ void stg_stream_u8(void *p, uint32_t v)
 {
     asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk copy (TMA engine, SASS UBLKCP): global -> shared, completion on an mbarrier.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint64_t global_ns()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// watchdog for the two spin waits of the stream kernel: a wait that lasts longer than this is a bug
+// (or a lost co-residency guarantee); the kernel then raises a status bit and stops waiting so that
+// the launch always terminates.
+constexpr uint64_t kWatchdogNs = 2000000000ull;
+
+// returns false when the watchdog expired
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (done) return true;
+        const uint64_t now = global_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kWatchdogNs) return false;
+    }
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// bytes: multiple of 16, > 0; src and dst 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -69,7 +148,7 @@ __device__ __forceinline__ unsigned long long desc_peek(const unsigned long long
 //   changed <=> |cur - ref| > thr  (server/include/common.h:14 LR_THRESHOLDS; test.cu:565)
 // ad   = per-byte absolute difference
 // addc = per-byte constant, hi = false: (128 - (thr+1)) for thr <= 127
-//                           hi = true : (256 - (thr+1)) for 128 <= thr <= 254, 0 for thr = 255
+//                           hi = true : (256 - (thr+1)) for 128 <= thr <= 254, 0x00 never matches for thr = 255
 // returns 0x80 in every byte lane that changed.
 // ------------------------------------------------------------------------------------------
 template <bool HI>

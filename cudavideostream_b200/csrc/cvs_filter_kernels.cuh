@@ -1,0 +1,329 @@
+// cvs_filter_kernels.cuh -- the kernels around the fused stream kernel: noise filter, text overlay,
+// binarisation pass 2, stand-alone display filters, client-side apply and the synthetic camera.
+#pragma once
+#include "cvs_pixel.cuh"
+
+namespace cvs {
+
+// ------------------------------------------------------------------------------------------------
+// A10 noise filter: K x K zero-padded convolution per channel, fp32 accumulation with one FFMA per
+// tap in row-major tap order, truncation to u8.   (loop structure of server/src/kernels.cu:119-134;
+// nvcc contracts "acc += k*p" into FFMA, which is what reproduces REPORT/report.tex:2351-2378.)
+//
+// The frame is treated as an H x 3W byte image in which the horizontal neighbour of a byte is 3
+// bytes away.  Fast path (3W % 4 == 0): a thread produces 4 consecutive output bytes; it fetches,
+// for each of the K tap rows, the aligned words that cover bytes [x - 3(K/2), x + 3 + 3(K/2)] through
+// L1 (neighbouring threads share them) and converts each byte to float once.
+// ------------------------------------------------------------------------------------------------
+struct ConvWeights {
+    float k[81];
+};
+
+__device__ __forceinline__ uint32_t trunc_u8(float acc)
+{
+    // (uint8_t)acc as x86-64 compiles it: cvttss2si to a 32-bit integer, low byte
+    return (uint32_t)__float2int_rz(acc) & 0xffu;
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) k_conv_rows4(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                                    int width, int height, size_t in_stride, size_t out_stride,
+                                                    const __grid_constant__ ConvWeights w)
+{
+    constexpr int R = K / 2;
+    constexpr int HALO = 3 * R;                      // bytes on each side
+    constexpr int WL = (HALO + 3) / 4;               // whole words on each side
+    constexpr int NW = 1 + 2 * WL;                   // words fetched per tap row
+    const int rowbytes = 3 * width;
+    const int wordsperrow = rowbytes >> 2;
+    const int xw = blockIdx.x * blockDim.x + threadIdx.x; // word column
+    const int row = blockIdx.y;
+    const uint8_t *fin = in + (size_t)blockIdx.z * in_stride;
+    uint8_t *fout = out + (size_t)blockIdx.z * out_stride;
+    if (xw >= wordsperrow) return;
+
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+        const int rr = row + i - R;
+        uint32_t wd[NW];
+        if (rr >= 0 && rr < height) {
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(fin + (size_t)rr * rowbytes);
+#pragma unroll
+            for (int u = 0; u < NW; u++) {
+                const int xi = xw + u - WL;
+                wd[u] = (xi >= 0 && xi < wordsperrow) ? __ldg(rp + xi) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < NW; u++) wd[u] = 0u;
+        }
+        // bytes at offsets [-HALO, 3 + HALO] relative to x = 4*xw  <->  byte index (4*WL - HALO) + n of wd[]
+        float f[4 + 2 * HALO];
+#pragma unroll
+        for (int n = 0; n < 4 + 2 * HALO; n++) {
+            const int bi = 4 * WL - HALO + n;
+            f[n] = (float)((wd[bi >> 2] >> (8 * (bi & 3))) & 0xffu);
+        }
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const float kw = w.k[i * K + j];
+#pragma unroll
+            for (int o = 0; o < 4; o++) acc[o] = __fmaf_rn(kw, f[o + 3 * j], acc[o]);
+        }
+    }
+    uint32_t pk = trunc_u8(acc[0]) | (trunc_u8(acc[1]) << 8) | (trunc_u8(acc[2]) << 16) | (trunc_u8(acc[3]) << 24);
+    reinterpret_cast<uint32_t *>(fout + (size_t)row * rowbytes)[xw] = pk;
+}
+
+// generic path: any width, one output byte per thread
+__global__ void __launch_bounds__(256) k_conv_bytes(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int width,
+                                                    int height, size_t in_stride, size_t out_stride, int K,
+                                                    const __grid_constant__ ConvWeights w)
+{
+    const int rowbytes = 3 * width;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (x >= rowbytes) return;
+    const uint8_t *fin = in + (size_t)blockIdx.z * in_stride;
+    uint8_t *fout = out + (size_t)blockIdx.z * out_stride;
+    const int R = K / 2;
+    float acc = 0.f;
+    for (int i = 0; i < K; i++)
+        for (int j = 0; j < K; j++) {
+            const int rr = row + i - R, xx = x + 3 * (j - R);
+            float pix = 0.f;
+            if (rr >= 0 && rr < height && xx >= 0 && xx < rowbytes) pix = (float)fin[(size_t)rr * rowbytes + xx];
+            acc = __fmaf_rn(w.k[i * K + j], pix, acc);
+        }
+    fout[(size_t)row * rowbytes + x] = (uint8_t)trunc_u8(acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// text overlay: glyph idx[j] is blitted to rows [0, gh), byte columns [j*gw*3, (j+1)*gw*3)
+//                                                (server/src/kernels.cu:337-348 and host loop :466-476)
+// ------------------------------------------------------------------------------------------------
+struct OverlayText {
+    int n;
+    signed char idx[252]; // glyph index per character, -1 = not in the atlas (skipped)
+};
+
+__global__ void __launch_bounds__(256) k_overlay(uint8_t *frames, size_t stride, int width, const uint8_t *__restrict__ glyphs,
+                                                 int gw, int gh, const __grid_constant__ OverlayText txt)
+{
+    const int j = blockIdx.y; // character
+    const int g = txt.idx[j];
+    if (g < 0) return;
+    const int mw = 3 * gw, area = mw * gh;
+    const int offset = j * mw;
+    if (offset + mw > 3 * width) return;
+    uint8_t *f = frames + (size_t)blockIdx.z * stride;
+    const uint8_t *m = glyphs + (size_t)g * area;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < area; i += gridDim.x * blockDim.x) {
+        const int y = i / mw, x = offset + i - y * mw;
+        f[(size_t)y * 3 * width + x] = m[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A7 "two max" threshold: the CPU loop restated literally (server/src/server.cpp:108-127), one
+// thread per frame.  ht: [nframes][256] histogram; thr: [nframes].
+// ------------------------------------------------------------------------------------------------
+__global__ void k_threshold(const unsigned int *__restrict__ hist, int *__restrict__ thr, int nframes, int clamp_lo,
+                            int clamp_hi)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nframes) return;
+    const unsigned int *h = hist + (size_t)t * 256;
+    long long mx = -1;
+    int imax = -1, isec = -1;
+    for (int i = 0; i < 256; i++) {
+        const long long v = (long long)h[i];
+        if (v >= mx) { // the else-branch of the reference can never fire: sec_max is set to the new max
+            isec = imax;
+            imax = i;
+            mx = v;
+        }
+    }
+    int th = (imax + isec) / 2;
+    if (th < clamp_lo) th = clamp_lo;
+    if (th > clamp_hi) th = clamp_hi;
+    thr[t] = th;
+}
+
+// A6 binarize pass 2: gray1 (1 B/pixel) -> 3-channel 0/255 image   (server.cpp:129-135)
+__global__ void __launch_bounds__(256) k_binarize_expand(const uint8_t *__restrict__ gray1, size_t gray_stride,
+                                                         uint8_t *__restrict__ out, size_t out_stride,
+                                                         const int *__restrict__ thr, uint32_t npix)
+{
+    const uint32_t ngroups = (npix + kGroupPixels - 1) / kGroupPixels;
+    const int t = blockIdx.y;
+    const int th = thr[t];
+    const uint8_t *g = gray1 + (size_t)t * gray_stride;
+    uint8_t *o = out + (size_t)t * out_stride;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+        const uint32_t px0 = gi * kGroupPixels;
+        const uint32_t npx = min(npix - px0, (uint32_t)kGroupPixels);
+        uint32_t gw[4] = {0, 0, 0, 0};
+        if (npx == (uint32_t)kGroupPixels) {
+            uint4 v = *reinterpret_cast<const uint4 *>(g + px0);
+            gw[0] = v.x; gw[1] = v.y; gw[2] = v.z; gw[3] = v.w;
+        } else {
+            for (uint32_t i = 0; i < npx; i++) gw[i >> 2] |= (uint32_t)g[px0 + i] << (8 * (i & 3));
+        }
+        uint32_t ow[kGroupWords];
+#pragma unroll
+        for (int k = 0; k < kGroupWords; k++) ow[k] = 0;
+#pragma unroll
+        for (int px = 0; px < kGroupPixels; px++) {
+            const int gv = (int)((gw[px >> 2] >> (8 * (px & 3))) & 0xffu);
+            put_pixel(ow, px, gv > th ? 0xffffffu : 0u);
+        }
+        store_group(o + (size_t)px0 * 3, ow, npx * 3);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone display filters on a frame pair / a frame (the micro-benchmarks of tests/heat_map_*,
+// tests/grayscale-*, tests/binarization).  Grid-stride over 48-byte groups.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_group(const uint8_t *src, uint32_t (&w)[kGroupWords], uint32_t nv)
+{
+    if (nv >= (uint32_t)kGroupBytes) {
+        const uint4 *s = reinterpret_cast<const uint4 *>(src);
+        uint4 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kGroupWords; k++) w[k] = 0;
+#pragma unroll
+        for (int j = 0; j < kGroupBytes; j++)
+            if ((uint32_t)j < nv) w[j >> 2] |= (uint32_t)src[j] << (8 * (j & 3));
+    }
+}
+
+// OP: 0 heat map (prev, cur), 1 red map (prev, cur, threshold), 2 gray avg 3ch, 3 gray weighted 3ch,
+//     4 gray avg 1ch, 5 gray weighted 1ch
+template <int OP, bool HI>
+__global__ void __launch_bounds__(256) k_filter(const uint8_t *__restrict__ prev, const uint8_t *__restrict__ cur,
+                                                uint8_t *__restrict__ out, uint32_t nbytes, uint32_t addc,
+                                                const uint32_t *__restrict__ lut_g, unsigned int *hist)
+{
+    __shared__ uint32_t slut[768];
+    __shared__ uint32_t shist[256];
+    if (OP == 0)
+        for (uint32_t i = threadIdx.x; i < 766; i += blockDim.x) slut[i] = lut_g[i];
+    if (OP >= 4 && hist)
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) shist[i] = 0;
+    __syncthreads();
+    const uint32_t ngroups = (nbytes + kGroupBytes - 1) / kGroupBytes;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+        const uint32_t goff = gi * kGroupBytes;
+        const uint32_t nv = min(nbytes - goff, (uint32_t)kGroupBytes);
+        uint32_t c[kGroupWords], o[kGroupWords];
+        load_group(cur + goff, c, nv);
+        if (OP == 0 || OP == 1) {
+            uint32_t r[kGroupWords];
+            load_group(prev + goff, r, nv);
+            if (OP == 0) {
+                uint32_t ad[kGroupWords];
+#pragma unroll
+                for (int k = 0; k < kGroupWords; k++) ad[k] = absdiff4(c[k], r[k]);
+                group_heat(ad, slut, o);
+            } else {
+                uint32_t mk[kGroupWords];
+#pragma unroll
+                for (int k = 0; k < kGroupWords; k++) mk[k] = changed80<HI>(absdiff4(c[k], r[k]), addc);
+                group_red<false>(mk, r, o);
+            }
+            store_group(out + goff, o, nv);
+        } else if (OP == 2 || OP == 3) {
+            group_gray3<OP == 3>(c, o);
+            store_group(out + goff, o, nv);
+        } else {
+            uint32_t g4[4];
+            group_gray1<OP == 5>(c, g4);
+            const uint32_t npx = nv / 3u;
+            uint8_t *gd = out + goff / 3u;
+            if (npx == (uint32_t)kGroupPixels) stg_stream(gd, make_uint4(g4[0], g4[1], g4[2], g4[3]));
+#pragma unroll
+            for (int px = 0; px < kGroupPixels; px++)
+                if ((uint32_t)px < npx) {
+                    const uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                    if (npx != (uint32_t)kGroupPixels) gd[px] = (uint8_t)gv;
+                    if (hist) atomicAdd(&shist[gv], 1u);
+                }
+        }
+    }
+    if (OP >= 4 && hist) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x)
+            if (shist[i]) atomicAdd(hist + i, shist[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// client side of the wire format: frame[xs[i]] += diff[i]   (client/opencv.cpp:64-66)
+// xs is strictly ascending, so no two entries touch the same byte.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_client_apply(uint8_t *frame, const int *__restrict__ xs,
+                                                      const uint8_t *__restrict__ diff,
+                                                      const unsigned int *__restrict__ pos, size_t capacity)
+{
+    size_t n = *pos;
+    if (n > capacity) n = capacity;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = xs[i];
+        frame[x] = (uint8_t)(frame[x] + diff[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic camera; numpy twin: cudavideostream_b200/synth.py
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint8_t synth_base_byte(uint64_t seed, uint32_t i, int width, int height)
+{
+    const uint32_t px = i / 3u, ch = i - 3u * px;
+    const uint32_t x = px % (uint32_t)width, y = px / (uint32_t)width;
+    const uint32_t den = (uint32_t)(width + height - 2);
+    const int grad = den ? (int)(((x + y) * 255u) / den) : 0;
+    const uint64_t h = splitmix64(seed + (uint64_t)i);
+    int v = grad + (int)(h & 63u) - 32 + 3 * (int)ch;
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    return (uint8_t)v;
+}
+
+__host__ __device__ __forceinline__ uint8_t synth_next_byte(uint64_t key, uint32_t i, uint8_t prev, uint32_t density_ppm)
+{
+    const uint64_t h = splitmix64(key + (uint64_t)i);
+    const uint32_t u = (uint32_t)(h & 0xFFFFFu);
+    int v;
+    if ((((uint64_t)u * 1000000ull) >> 20) < (uint64_t)density_ppm) {
+        const int delta = 21 + (int)((h >> 20) % 60u);
+        const bool up = (h >> 40) & 1u;
+        v = up ? prev + delta : prev - delta;
+        if (v > 255) v = prev - delta;
+        if (v < 0) v = prev + delta;
+    } else {
+        v = (int)prev + (int)((h >> 24) % 7u) - 3;
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    }
+    return (uint8_t)v;
+}
+
+__global__ void __launch_bounds__(256) k_synth_base(uint8_t *out, uint32_t nbytes, int width, int height, uint64_t seed)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += gridDim.x * blockDim.x)
+        out[i] = synth_base_byte(seed, i, width, height);
+}
+
+__global__ void __launch_bounds__(256) k_synth_next(const uint8_t *__restrict__ prev, uint8_t *out, uint32_t nbytes,
+                                                    uint64_t key, uint32_t density_ppm)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += gridDim.x * blockDim.x)
+        out[i] = synth_next_byte(key, i, prev[i], density_ppm);
+}
+
+} // namespace cvs

@@ -25,6 +25,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 #define CVS_ABI_VERSION 1
 
@@ -107,6 +110,10 @@ cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *tex
 cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text,
                       unsigned int *pos, int *xs, uint64_t *ticket);
 cvs_status cvs_wait(cvs_handle h, uint64_t ticket);
+/* cvs_submit with the payload bytes written to a separate buffer instead of over the head of the input
+ * frame (which is then left untouched): for callers that keep captured frames in a pinned ring. */
+cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show,
+                         const char *text, unsigned int *pos, int *xs, uint64_t *ticket);
 
 /* device times of the most recent completed cvs_exec / cvs_wait, microseconds (CUDA events):
  * host-to-device copy, kernels, device-to-host copies -- reported separately, as the
@@ -153,10 +160,11 @@ cvs_status cvs_red_map_device(const uint8_t *d_prev, const uint8_t *d_cur, uint8
 cvs_status cvs_grayscale_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height,
                                 int weighted, int channels, void *cuda_stream);
 /* gray (weighted or average) -> 256-bin histogram -> two-max threshold clamped to
- * [clamp_lo, clamp_hi] -> 3-channel 0/255 image.  d_hist_thr: 257 ints of scratch/out
- * (histogram[256], threshold). */
-cvs_status cvs_binarize_device(const uint8_t *d_frame, uint8_t *d_out, int *d_hist_thr, int width,
-                               int height, int weighted, int clamp_lo, int clamp_hi,
+ * [clamp_lo, clamp_hi] -> 3-channel 0/255 image  (server.cpp:96-135, tests/binarization/cpu.cu).
+ * d_gray: width*height bytes (rounded up to 16) of scratch/out, the 1-channel gray image;
+ * d_hist_thr: 257 ints of scratch/out (histogram[256], threshold). */
+cvs_status cvs_binarize_device(const uint8_t *d_frame, uint8_t *d_out, uint8_t *d_gray, int *d_hist_thr,
+                               int width, int height, int weighted, int clamp_lo, int clamp_hi,
                                void *cuda_stream);
 /* K x K zero-padded convolution, fp32 FMA accumulation in row-major tap order, truncation */
 cvs_status cvs_noise_filter_device(const uint8_t *d_frame, uint8_t *d_out, int width, int height,
@@ -177,6 +185,9 @@ cvs_status cvs_synth_next_device(const uint8_t *d_prev, uint8_t *d_out, int widt
                                  uint64_t seed, uint32_t frame_index, uint32_t density_ppm,
                                  void *cuda_stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif
