@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 nproc > gpurun_out/host.txt; grep -m1 "model name" /proc/cpuinfo >> gpurun_out/host.txt
-timeout 900 python -m pytest tests -q -m gpu --timeout 180 -x ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu --timeout 180 ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log

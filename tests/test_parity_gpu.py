@@ -63,7 +63,7 @@ def test_threshold_edges(cvs, oracle):
 @pytest.mark.parametrize("thr", [-1, 0, 1, 20, 127, 128, 200, 254, 255])
 def test_threshold_values(cvs, oracle, thr):
     base, frames = random_sequence(40, 30, 2, 0.3, seed=thr + 7)
-    frames[1] = np.random.default_rng(thr).integers(0, 256, size=frames[1].size, dtype=np.uint8)
+    frames[1] = np.random.default_rng(thr + 1).integers(0, 256, size=frames[1].size, dtype=np.uint8)
     _check_frames(cvs, oracle, 40, 30, base, frames, threshold=thr)
 
 
