@@ -17,7 +17,7 @@
 #include <string>
 
 #include "cvs_filter_kernels.cuh"
-#include "cvs_stream_kernel.cuh"
+#include "cvs_stream.cuh"
 
 namespace {
 
@@ -150,6 +150,7 @@ struct cvs_stream_s {
     size_t Npad = 0, P16 = 0;
     bool hi = false;
     uint32_t addc = 0;
+    uint32_t debug = 0; // CVS_DEBUG_FLAGS (profiling experiments only)
     cvs::ConvWeights weights;
     int sms = 0;
     // glyph atlas
@@ -360,6 +361,7 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.desc = h->d_desc;
         p.epoch = h->epoch;
         p.addc = h->addc;
+        p.debug = h->debug;
         p.status = h->d_status;
         void *args[] = {&p};
         CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(cvs::kThreads), args,
@@ -463,6 +465,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     h->Npad = (size_t)h->ngroups * cvs::kGroupBytes;
     h->P16 = round_up(h->npix, 16);
     threshold_consts(cfg->threshold, h->hi, h->addc);
+    if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
     CU_TRY(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device));

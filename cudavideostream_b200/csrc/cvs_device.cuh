@@ -168,6 +168,14 @@ __device__ __forceinline__ uint32_t spread80(uint32_t m80)
 
 __device__ __forceinline__ uint32_t absdiff4(uint32_t a, uint32_t b) { return __vabsdiffu4(a, b); }
 
+// per-byte a - b (mod 256): the payload value df & 0xFF of test.cu:566.  Bit 7 of every byte lane of the
+// minuend is forced on and cleared in the subtrahend so no borrow crosses a lane; the true bit 7 is patched in.
+__device__ __forceinline__ uint32_t sub4(uint32_t a, uint32_t b)
+{
+    const uint32_t t = (a | 0x80808080u) - (b & 0x7f7f7f7fu);
+    return t ^ ((a ^ ~b) & 0x80808080u);
+}
+
 // horizontal sum of the four byte lanes (each lane <= 63 so the sum fits)
 __device__ __forceinline__ uint32_t hsum4(uint32_t x) { return (x * 0x01010101u) >> 24; }
 

@@ -1,0 +1,480 @@
+// cvs_stream.cuh -- the fused hot path: thresholded difference + negative feedback +
+// ordered compaction (+ one display filter), as ONE persistent launch over a sequence of frames.
+//
+// Replaces kernel2 (server/src/kernels.cu:289-334), its CPU twin (tests/cuda_streaming/
+// test.cu:560-576) and the visualiser kernels that read the same frame pair (kernels.cu:31-95,
+// 243-281).  nframes = 1 is the drop-in exec_core path; nframes = T walks a device-resident
+// sequence (frame t+1 is differenced against the reference frame t left behind).
+//
+// Work decomposition
+//   * a frame is cut into groups of 48 B = 16 BGR pixels = three 16-byte vectors (cvs_pixel.cuh);
+//   * the grid is G persistent blocks of 512 threads, all co-resident (cooperative launch).  A frame
+//     is covered in nseg passes ("segments") of G*gps groups; in segment s block b owns the gps
+//     consecutive groups starting at (s*G + b)*gps and thread i of the block owns group i of that
+//     slice -- the SAME bytes in every frame.  One (frame, segment) pair is a "step";
+//   * ingest: thread 0 of a block streams the block's slice of the coming steps into a 3-stage
+//     shared-memory ring with 1-D bulk copies (TMA engine, cp.async.bulk + mbarrier, L2 evict-first):
+//     every byte of a frame crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each
+//     thread picks its 16 whole pixels out of shared memory with three conflict-free LDS.128;
+//   * reference: when a frame fits one segment (1080p on 148 SMs) the thread's 48 reference bytes
+//     live in registers for the whole sequence (REFREG): HBM never sees the reference between the
+//     first frame and the last.  Otherwise each thread reloads / rewrites its own 48 bytes with
+//     L2 evict-last accesses (the reference frame stays L2 resident; same thread, same address, so
+//     no cross-thread hazard exists);
+//   * one pass over the 12 words of a group produces, per word: byte-SIMD |cur-ref| > T flags, the
+//     4-bit change nibble (one multiply gathers the four flag bits) merged into a 48-bit change mask,
+//     the difference bytes cur-ref (parked in the thread's own 48 bytes of the ring stage) and the
+//     updated reference (negative feedback).  popc of the mask is the thread's entry count;
+//   * compaction: warp shuffle scan + one block scan; cross-block offsets by a one-round decoupled
+//     look-back: each block publishes (epoch<<32 | count) for the step and sums the descriptors of
+//     its predecessors, each read by its own thread; the running total of earlier segments of the
+//     frame travels in one extra descriptor.  A thread then walks the set bits of its mask and stages
+//     (index, value) in shared memory in rank order; the block flushes with 16-byte (xs) / 4-byte
+//     (diff) fully coalesced streaming stores;
+//   * display filter MODE (heat map, red maps, grayscale, binarisation pass 1) is computed from the
+//     same registers and written with 16-byte streaming stores;
+//   * the step loop is software-pipelined: while a block runs the front half of step q (ingest ... publish)
+//     the descriptors it needs for step q-1 are already in flight, and the back half of step q-1 (staging
+//     and flush) follows, so neither the L2 round trip of the look-back nor a late predecessor stalls it.
+//
+// Order, values and the new reference are bit-exact with oracle/cvs_oracle.c orc_diff_compact;
+// unlike kernel2 the payload order is deterministic (ascending byte index).
+#pragma once
+#include "cvs_pixel.cuh"
+
+namespace cvs {
+
+constexpr int kThreads = 512;                         // threads per block
+constexpr int kWarps = kThreads / 32;
+constexpr int kStageBytes = kThreads * kGroupBytes;   // 24,576 B: one block slice
+constexpr int kStages = 3;
+constexpr int kStageEntries = 4096;                   // payload entries staged per flush round
+
+enum StatusBits : unsigned { kStatusCapacity = 1u, kStatusWatchdog = 2u };
+
+struct StreamParams {
+    const uint8_t *frames;      // frame t at frames + t*frame_stride (16-byte aligned)
+    size_t frame_stride;        // multiple of 16, >= nbytes rounded up to 16
+    int nframes;
+    uint8_t *ref;               // reference frame, padded to ngroups*48 bytes
+    uint32_t nbytes;            // N = 3*W*H
+    uint32_t nbytes16;          // N rounded up to 16
+    uint32_t ngroups;           // ceil(N / 48)
+    uint32_t nseg;              // segments per frame
+    uint32_t gps;               // groups per block per segment (<= kThreads)
+    unsigned int *pos;          // [nframes]
+    int *xs;                    // frame t at xs + t*cap
+    uint8_t *diff;              // frame t at diff + t*cap
+    size_t cap;                 // payload capacity per frame (entries)
+    uint8_t *show;              // display frame t at show + t*show_stride (MODE 1,2,3,4,6)
+    size_t show_stride;
+    uint8_t *gray1;             // MODE 5/7: one gray byte per pixel, frame t at gray1 + t*gray_stride
+    size_t gray_stride;
+    unsigned int *hist;         // MODE 5/7: [nframes][256], zeroed by the host before the launch
+    const uint32_t *heat_lut;   // MODE 1: 766 entries B | G<<8 | R<<16
+    unsigned long long *desc;   // [nframes*nseg][G+1]
+    uint32_t epoch;             // tag of this launch
+    uint32_t addc;              // threshold constant for changed80<>
+    unsigned int *status;       // StatusBits
+    uint32_t debug;             // profiling experiments only (CVS_DEBUG_FLAGS): 1 no look-back, 2 no emission
+};
+
+// dynamic shared memory layout (bytes)
+struct SmemLayout {
+    static constexpr int stage = 0;                                        // kStages * kStageBytes
+    static constexpr int sxs = kStages * kStageBytes;                      // (kStageEntries + 4) ints
+    static constexpr int sd = sxs + (kStageEntries + 4) * 4;               // kStageEntries + 16 bytes
+    static constexpr int lut = sd + kStageEntries + 16;                    // 768 words
+    static constexpr int hist = lut + 768 * 4;                             // 256 words
+    static constexpr int wtot = hist + 256 * 4;                            // 2 x kWarps words (by step parity)
+    static constexpr int red = wtot + 2 * kWarps * 4;                      // 2 x kWarps words
+    static constexpr int bar = red + 2 * kWarps * 4;                       // kStages mbarriers
+    static constexpr int total = bar + kStages * 8;
+};
+static_assert(SmemLayout::bar % 8 == 0, "mbarrier alignment");
+static_assert(SmemLayout::sd % 16 == 0 && SmemLayout::sxs % 16 == 0, "staging alignment");
+
+// Coalesced flush of n staged entries to global rank g0.  The staging arrays were filled starting
+// at element (g0 & 3), so that 16-byte vectors of xs (and 4-byte words of diff) line up between
+// shared and global memory.
+__device__ __forceinline__ void flush_payload(const int *sxs, const uint8_t *sd, int *xs_out, uint8_t *df_out,
+                                              size_t g0, uint32_t n, size_t cap, uint32_t tid)
+{
+    if (g0 >= cap) return;
+    if (g0 + n > cap) n = (uint32_t)(cap - g0);
+    const uint32_t sh = (uint32_t)(g0 & 3);
+    // element e of the staging arrays <-> global rank (g0 - sh) + e ; valid e in [sh, sh + n)
+    int *xg = xs_out + (g0 - sh);
+    uint8_t *dg = df_out + (g0 - sh);
+    const uint32_t end = sh + n;
+    const uint32_t body0 = sh ? 4u : 0u;      // first fully valid quad
+    const uint32_t body1 = end & ~3u;         // end of the last fully valid quad
+    if (body1 > body0) {
+        const uint32_t nq = (body1 - body0) >> 2;
+        for (uint32_t q = tid; q < nq; q += kThreads) {
+            const uint32_t e = body0 + 4 * q;
+            stg_stream(xg + e, *reinterpret_cast<const uint4 *>(sxs + e));
+            stg_stream_u32(dg + e, *reinterpret_cast<const uint32_t *>(sd + e));
+        }
+    }
+    // head [sh, min(4,end)) and tail [max(body1,body0), end): at most 3 + 3 entries
+    if (tid < 8) {
+        uint32_t e;
+        bool ok;
+        if (tid < 4) {
+            e = tid;
+            ok = sh && e >= sh && e < end && e < 4u;
+        } else {
+            e = (body1 > body0 ? body1 : body0) + (tid - 4);
+            ok = e < end && e >= sh && (body1 >= body0);
+            if (sh && body1 < 4u) ok = false; // everything sits in the head quad, already written
+        }
+        if (ok) {
+            stg_stream_u32(xg + e, (uint32_t)sxs[e]);
+            stg_stream_u8(dg + e, sd[e]);
+        }
+    }
+}
+
+// walks the set bits of `bits` (bit j <-> byte `jbase + j` of the group): index goes to sxs, the
+// difference byte is fetched from the thread's parked bytes at shared address dvaddr
+template <bool CHECKED>
+__device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_t goff, uint32_t dvaddr, int *sxs,
+                                          uint8_t *sd, uint32_t &o, uint32_t sh, uint32_t wn)
+{
+    while (bits) {
+        const uint32_t j = jbase + (uint32_t)__ffs((int)bits) - 1u;
+        bits &= bits - 1u;
+        if (!CHECKED || o - sh < wn) {
+            uint32_t v;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(dvaddr + j));
+            sxs[o] = (int)(goff + j);
+            sd[o] = (uint8_t)v;
+        }
+        o++;
+    }
+}
+
+template <int MODE, bool HI, bool REFREG>
+__global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    int *sxs = reinterpret_cast<int *>(smem + SmemLayout::sxs);
+    uint8_t *sd = smem + SmemLayout::sd;
+    uint32_t *slut = reinterpret_cast<uint32_t *>(smem + SmemLayout::lut);
+    uint32_t *shist = reinterpret_cast<uint32_t *>(smem + SmemLayout::hist);
+    uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + SmemLayout::wtot);
+    uint32_t *red = reinterpret_cast<uint32_t *>(smem + SmemLayout::red);
+    const uint32_t stage_addr = smem_u32(smem + SmemLayout::stage);
+    const uint32_t bar_addr = smem_u32(smem + SmemLayout::bar);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t b = blockIdx.x, G = gridDim.x;
+    const uint32_t N = p.nbytes;
+    const uint32_t nsteps = (uint32_t)p.nframes * p.nseg;
+    constexpr bool kBinarize = (MODE == kModeBinarize || MODE == kModeBinarizeAvg);
+    constexpr bool kGrayW = (MODE == kModeGrayWeighted || MODE == kModeBinarize);
+
+    uint32_t phase = 0;     // bit st: parity the next wait on stage st expects
+    bool tripped = false;   // watchdog expired once: stop waiting altogether
+
+    // slice of this block in segment s: byte offset and byte count of the bulk copy
+    auto slice = [&](uint32_t s, uint32_t &off, uint32_t &bytes) {
+        uint64_t g0 = ((uint64_t)s * G + b) * p.gps;
+        uint64_t o = g0 * kGroupBytes;
+        if (o >= p.nbytes16) { off = 0; bytes = 0; return; }
+        uint64_t e = o + (uint64_t)p.gps * kGroupBytes;
+        if (e > p.nbytes16) e = p.nbytes16;
+        off = (uint32_t)o;
+        bytes = (uint32_t)(e - o);
+    };
+    uint64_t pol = 0;
+    auto issue = [&](uint32_t q) { // thread 0 only
+        uint32_t t = q / p.nseg, s = q - t * p.nseg, off, bytes;
+        slice(s, off, bytes);
+        if (bytes) {
+            const uint32_t st = q % kStages;
+            // the stage was last written through the generic proxy (parked difference bytes)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar_addr + 8 * st, bytes);
+            bulk_g2s(stage_addr + st * kStageBytes, p.frames + (size_t)t * p.frame_stride + off, bytes,
+                     bar_addr + 8 * st, pol);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; i++) mbar_init(bar_addr + 8 * i, 1);
+        mbar_init_fence();
+    }
+    if (MODE == kModeHeat)
+        for (uint32_t i = tid; i < 766; i += kThreads) slut[i] = p.heat_lut[i];
+    __syncthreads();
+    if (tid == 0) {
+        pol = l2_policy_evict_first();
+        for (uint32_t q = 0; q < (uint32_t)kStages && q < nsteps; q++) issue(q);
+    }
+
+    uint32_t r[kGroupWords];
+    const uint64_t keep = l2_policy_evict_last();
+    bool dirty = false;
+    uint32_t goff = 0, nv = 0; // byte offset of this thread's group in the frame, valid bytes
+    auto geometry = [&](uint32_t s) {
+        uint64_t g = ((uint64_t)s * G + b) * p.gps + tid;
+        bool ok = tid < p.gps && g < p.ngroups;
+        goff = ok ? (uint32_t)(g * kGroupBytes) : 0u;
+        nv = ok ? min(N - goff, (uint32_t)kGroupBytes) : 0u;
+    };
+    auto load_ref = [&]() {
+        if (nv) {
+            uint4 a = ldg_keep(p.ref + goff, keep), bq = ldg_keep(p.ref + goff + 16, keep), cq = ldg_keep(p.ref + goff + 32, keep);
+            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+            r[4] = bq.x; r[5] = bq.y; r[6] = bq.z; r[7] = bq.w;
+            r[8] = cq.x; r[9] = cq.y; r[10] = cq.z; r[11] = cq.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kGroupWords; k++) r[k] = 0;
+        }
+    };
+    auto store_ref = [&]() {
+        stg_keep(p.ref + goff, make_uint4(r[0], r[1], r[2], r[3]), keep);
+        stg_keep(p.ref + goff + 16, make_uint4(r[4], r[5], r[6], r[7]), keep);
+        stg_keep(p.ref + goff + 32, make_uint4(r[8], r[9], r[10], r[11]), keep);
+    };
+
+    if (REFREG) { // nseg == 1: the geometry never changes
+        geometry(0);
+        load_ref();
+    }
+
+    // The loop is software-pipelined by one step: iteration q runs the FRONT half of step q (ingest, flags,
+    // change mask, feedback, counts, publish) and then the BACK half of step q-1 (look-back sum, staging,
+    // flush).  The predecessors' descriptors of step q-1 are fetched at the top of the iteration, so their L2
+    // round trip hides behind the front half, and one barrier serves both the block scan of step q and the
+    // look-back reduction of step q-1.
+    uint32_t b_lo = 0, b_hi = 0, b_lrank = 0, b_total = 0, b_goff = 0, b_myaddr = 0, b_t = 0, b_s = 0;
+    bool pending = false;
+    uint32_t t = 0, s = 0; // frame and segment of step q
+
+    for (uint32_t q = 0; q <= nsteps; q++) {
+        const bool front = q < nsteps;
+
+        // ---- back half, part 1: start fetching the look-back descriptors of step q-1.  Thread i < b reads
+        //      predecessor i; thread b reads the running total of the earlier segments of the frame
+        const unsigned long long *pd = nullptr;
+        unsigned long long pv = 0;
+        if (pending && !(p.debug & 1u)) {
+            const unsigned long long *prow = p.desc + (size_t)(q - 1) * (G + 1);
+            if (tid < b) pd = prow + tid;
+            else if (tid == b && b_s > 0) pd = prow - (G + 1) + G;
+            if (pd) pv = desc_peek(pd);
+        }
+
+        uint32_t lo = 0, hi = 0, cnt = 0, incl = 0, myaddr = 0;
+        if (front) {
+            const uint32_t st = q % kStages;
+            uint32_t soff, sbytes;
+            slice(s, soff, sbytes);
+            if (!REFREG) {
+                geometry(s);
+                load_ref(); // L2 hit; issued before the wait on the frame slice
+            }
+            if (kBinarize && s == 0) {
+                // the thread that zeroes bin i is the one that flushed it at the end of the previous frame;
+                // the barrier below orders the zeroing before this frame's atomics
+                for (uint32_t i = tid; i < 256; i += kThreads) shist[i] = 0;
+                __syncthreads();
+            }
+
+            // ---- 1. this thread's 16 pixels out of the ring
+            if (sbytes) {
+                // steps with an empty slice never touch the barrier, so the parity is tracked per stage
+                if (!tripped && !mbar_wait(bar_addr + 8 * st, (phase >> st) & 1u)) {
+                    tripped = true;
+                    atomicOr(p.status, kStatusWatchdog);
+                }
+                phase ^= 1u << st;
+            }
+            myaddr = stage_addr + st * kStageBytes + tid * kGroupBytes;
+            uint32_t c[kGroupWords];
+            if (nv) {
+                uint4 x = lds128(myaddr), y = lds128(myaddr + 16), z = lds128(myaddr + 32);
+                c[0] = x.x; c[1] = x.y; c[2] = x.z; c[3] = x.w;
+                c[4] = y.x; c[5] = y.y; c[6] = y.z; c[7] = y.w;
+                c[8] = z.x; c[9] = z.y; c[10] = z.z; c[11] = z.w;
+                if (nv < (uint32_t)kGroupBytes) { // the group that holds the end of the frame: bytes past N never differ
+#pragma unroll
+                    for (int k = 0; k < kGroupWords; k++) {
+                        const int vb = (int)nv - 4 * k;
+                        const uint32_t vm = vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << (8 * vb)) - 1u));
+                        c[k] = (c[k] & vm) | (r[k] & ~vm);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kGroupWords; k++) c[k] = r[k];
+            }
+
+            // ---- 2. display filter on the same registers (reference as it was BEFORE this frame)
+            if (MODE != kModeNone && nv) {
+                uint32_t o[kGroupWords];
+                if (MODE == kModeHeat) {
+                    uint32_t ad[kGroupWords];
+#pragma unroll
+                    for (int k = 0; k < kGroupWords; k++) ad[k] = absdiff4(c[k], r[k]);
+                    group_heat(ad, slut, o);
+                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
+                } else if (MODE == kModeRedBlack || MODE == kModeRedOverlap) {
+                    uint32_t mk[kGroupWords];
+#pragma unroll
+                    for (int k = 0; k < kGroupWords; k++) mk[k] = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
+                    group_red<MODE == kModeRedOverlap>(mk, r, o);
+                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
+                } else if (MODE == kModeGrayWeighted || MODE == kModeGrayAverage) {
+                    group_gray3<kGrayW>(c, o);
+                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
+                } else if (kBinarize) {
+                    uint32_t g4[4];
+                    group_gray1<kGrayW>(c, g4);
+                    const uint32_t npx = nv / 3u; // whole pixels of this group inside the frame
+                    uint8_t *gdst = p.gray1 + (size_t)t * p.gray_stride + goff / 3u;
+                    if (npx == (uint32_t)kGroupPixels) stg_keep(gdst, make_uint4(g4[0], g4[1], g4[2], g4[3]), keep);
+#pragma unroll
+                    for (int px = 0; px < kGroupPixels; px++) {
+                        if ((uint32_t)px < npx) {
+                            uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                            if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
+                            atomicAdd(&shist[gv], 1u); // server.cpp:103-106
+                        }
+                    }
+                }
+            }
+
+            // ---- 3. one pass: flags -> 48-bit change mask, difference bytes, negative feedback
+            //         reference := changed ? current : reference                      (test.cu:565-570)
+            {
+                uint32_t dv[kGroupWords];
+#pragma unroll
+                for (int k = 0; k < kGroupWords; k++) {
+                    const uint32_t m = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
+                    // flag bits 7,15,23,31 -> adjacent bits 28..31 (all partial products land on distinct bits)
+                    const uint32_t nib = m * 0x00204081u;
+                    if (k < 8) lo |= (nib >> (28 - 4 * k)) & (0xFu << (4 * k));
+                    else hi |= (nib >> (28 - 4 * (k - 8))) & (0xFu << (4 * (k - 8)));
+                    dv[k] = sub4(c[k], r[k]);
+                    const uint32_t fm = spread80(m);
+                    r[k] = (c[k] & fm) | (r[k] & ~fm);
+                }
+                if (nv < (uint32_t)kGroupBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
+                    lo &= nv >= 32u ? 0xffffffffu : ((1u << nv) - 1u);
+                    hi &= nv <= 32u ? 0u : ((1u << (nv - 32u)) - 1u);
+                }
+                if (lo | hi) {
+                    // park the difference bytes in this thread's own 48 bytes of the stage
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr), "r"(dv[0]), "r"(dv[1]), "r"(dv[2]), "r"(dv[3]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 16), "r"(dv[4]), "r"(dv[5]), "r"(dv[6]), "r"(dv[7]) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 32), "r"(dv[8]), "r"(dv[9]), "r"(dv[10]), "r"(dv[11]) : "memory");
+                    if (REFREG) dirty = true;
+                    else store_ref();
+                }
+            }
+            cnt = (uint32_t)__popc(lo) + (uint32_t)__popc(hi);
+            incl = warp_incl_scan(cnt, lane);
+            if (lane == 31) wtot[(q & 1u) * kWarps + warp] = incl;
+        }
+
+        // ---- back half, part 2: the descriptors fetched at the top (retry in the rare case a predecessor
+        //      had not published yet)
+        if (pending) {
+            uint32_t part = 0;
+            if (pd) {
+                if ((uint32_t)(pv >> 32) != p.epoch) {
+                    const uint64_t t0 = global_ns();
+                    do {
+                        __nanosleep(40);
+                        pv = desc_peek(pd);
+                        if ((uint32_t)(pv >> 32) == p.epoch || tripped) break;
+                        if (global_ns() - t0 > kWatchdogNs) {
+                            tripped = true;
+                            atomicOr(p.status, kStatusWatchdog);
+                        }
+                    } while (true);
+                }
+                part = (uint32_t)pv;
+            }
+            // G <= kThreads is enforced by the host, so one pass covers every predecessor
+            part = warp_sum(part);
+            if (lane == 0) red[(q & 1u) * kWarps + warp] = part;
+        }
+
+        __syncthreads(); // S1: warp totals of step q and look-back partial sums of step q-1
+
+        uint32_t total = 0, lrank = 0;
+        if (front) {
+            uint32_t wv = lane < (uint32_t)kWarps ? wtot[(q & 1u) * kWarps + lane] : 0u;
+            uint32_t winc = warp_incl_scan(wv, lane);
+            total = __shfl_sync(0xffffffffu, winc, kWarps - 1);
+            const uint32_t wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
+            lrank = wexc + incl - cnt; // rank of this thread's first entry inside the block
+            if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
+        }
+
+        if (pending) {
+            uint32_t base;
+            {
+                uint32_t v = lane < (uint32_t)kWarps ? red[(q & 1u) * kWarps + lane] : 0u;
+                base = warp_sum(v);
+            }
+            if (tid == 0) {
+                if (b == G - 1) {
+                    desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
+                    if (b_s == p.nseg - 1) p.pos[b_t] = base + b_total;
+                }
+                if ((size_t)base + b_total > p.cap) atomicOr(p.status, kStatusCapacity);
+            }
+
+            // ---- stage (index, value) of step q-1 in rank order and flush; rounds of kStageEntries
+            int *xs_out = p.xs + (size_t)b_t * p.cap;
+            uint8_t *df_out = p.diff + (size_t)b_t * p.cap;
+            const uint32_t b_cnt = (uint32_t)__popc(b_lo) + (uint32_t)__popc(b_hi);
+            for (uint32_t w0 = 0; w0 < ((p.debug & 2u) ? 0u : b_total); w0 += kStageEntries) {
+                const uint32_t wn = min(b_total - w0, (uint32_t)kStageEntries);
+                const size_t g0 = (size_t)base + w0;
+                const uint32_t sh = (uint32_t)(g0 & 3);
+                if (w0) __syncthreads(); // previous round flushed
+                if (b_cnt && b_lrank < w0 + wn && b_lrank + b_cnt > w0) {
+                    uint32_t o = b_lrank - w0 + sh; // wraps below zero for a thread that straddles the window start
+                    if (b_lrank >= w0 && b_lrank + b_cnt <= w0 + wn) {
+                        emit_bits<false>(b_lo, 0, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+                        emit_bits<false>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+                    } else {
+                        emit_bits<true>(b_lo, 0, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+                        emit_bits<true>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+                    }
+                }
+                __syncthreads(); // S2
+                flush_payload(sxs, sd, xs_out, df_out, g0, wn, p.cap, tid);
+            }
+            // the stage of step q-1 is drained: every thread consumed its pixels before S1 of that step and
+            // emitted its parked bytes before the last S2 (none were parked when the total was 0): refill it
+            if (tid == 0 && q - 1 + kStages < nsteps) issue(q - 1 + kStages);
+        }
+
+        if (front) {
+            if (kBinarize && s == p.nseg - 1) {
+                __syncthreads();
+                for (uint32_t i = tid; i < 256; i += kThreads)
+                    if (shist[i]) atomicAdd(p.hist + (size_t)t * 256 + i, shist[i]);
+            }
+            b_lo = lo; b_hi = hi; b_lrank = lrank; b_total = total; b_goff = goff; b_myaddr = myaddr; b_t = t; b_s = s;
+            pending = true;
+            if (++s == p.nseg) { s = 0; ++t; }
+        } else {
+            pending = false;
+        }
+    }
+
+    if (REFREG && dirty) store_ref();
+}
+
+} // namespace cvs
