@@ -17,7 +17,7 @@
 #include <string>
 
 #include "cvs_filter_kernels.cuh"
-#include "cvs_stream.cuh"
+#include "cvs_stream_kernel.cuh"
 
 namespace {
 

@@ -1,4 +1,4 @@
-// cvs_stream.cuh -- the fused hot path: thresholded difference + negative feedback +
+// cvs_stream_kernel.cuh -- the fused hot path: thresholded difference + negative feedback +
 // ordered compaction (+ one display filter), as ONE persistent launch over a sequence of frames.
 //
 // Replaces kernel2 (server/src/kernels.cu:289-334), its CPU twin (tests/cuda_streaming/
@@ -12,10 +12,10 @@
 //     is covered in nseg passes ("segments") of G*gps groups; in segment s block b owns the gps
 //     consecutive groups starting at (s*G + b)*gps and thread i of the block owns group i of that
 //     slice -- the SAME bytes in every frame.  One (frame, segment) pair is a "step";
-//   * ingest: thread 0 of a block streams the block's slice of the coming steps into a 3-stage
-//     shared-memory ring with 1-D bulk copies (TMA engine, cp.async.bulk + mbarrier, L2 evict-first):
-//     every byte of a frame crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each
-//     thread picks its 16 whole pixels out of shared memory with three conflict-free LDS.128;
+//   * ingest: a block streams its slice of the coming steps into a 3-stage shared-memory ring with
+//     1-D bulk copies (TMA engine, cp.async.bulk + mbarrier, L2 evict-first): every byte of a frame
+//     crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each thread picks its 16
+//     whole pixels out of shared memory with three conflict-free LDS.128;
 //   * reference: when a frame fits one segment (1080p on 148 SMs) the thread's 48 reference bytes
 //     live in registers for the whole sequence (REFREG): HBM never sees the reference between the
 //     first frame and the last.  Otherwise each thread reloads / rewrites its own 48 bytes with
@@ -25,17 +25,19 @@
 //     4-bit change nibble (one multiply gathers the four flag bits) merged into a 48-bit change mask,
 //     the difference bytes cur-ref (parked in the thread's own 48 bytes of the ring stage) and the
 //     updated reference (negative feedback).  popc of the mask is the thread's entry count;
-//   * compaction: warp shuffle scan + one block scan; cross-block offsets by a one-round decoupled
-//     look-back: each block publishes (epoch<<32 | count) for the step and sums the descriptors of
-//     its predecessors, each read by its own thread; the running total of earlier segments of the
-//     frame travels in one extra descriptor.  A thread then walks the set bits of its mask and stages
-//     (index, value) in shared memory in rank order; the block flushes with 16-byte (xs) / 4-byte
-//     (diff) fully coalesced streaming stores;
+//   * compaction: warp shuffle scan + one block scan (the only block-wide barrier of a step);
+//     cross-block offsets by a one-round decoupled look-back: each block publishes
+//     (epoch<<32 | count) for the step and sums the descriptors of its predecessors, each read by
+//     its own thread; the running total of earlier segments of the frame travels in one extra
+//     descriptor.  Each WARP then walks the set bits of its lanes' masks, stages (index, value) in
+//     its own shared-memory window in rank order and flushes it with 16-byte (xs) / 4-byte (diff)
+//     coalesced streaming stores -- warps drift apart freely, the last one to finish refills the stage;
 //   * display filter MODE (heat map, red maps, grayscale, binarisation pass 1) is computed from the
 //     same registers and written with 16-byte streaming stores;
-//   * the step loop is software-pipelined: while a block runs the front half of step q (ingest ... publish)
-//     the descriptors it needs for step q-1 are already in flight, and the back half of step q-1 (staging
-//     and flush) follows, so neither the L2 round trip of the look-back nor a late predecessor stalls it.
+//   * the step loop is software-pipelined: while a block runs the front half of step q (ingest ...
+//     publish) the descriptors it needs for step q-1 are already in flight, and the back half of
+//     step q-1 (staging and flush) follows, so neither the L2 round trip of the look-back nor a late
+//     predecessor stalls it.
 //
 // Order, values and the new reference are bit-exact with oracle/cvs_oracle.c orc_diff_compact;
 // unlike kernel2 the payload order is deterministic (ascending byte index).
@@ -48,7 +50,7 @@ constexpr int kThreads = 512;                         // threads per block
 constexpr int kWarps = kThreads / 32;
 constexpr int kStageBytes = kThreads * kGroupBytes;   // 24,576 B: one block slice
 constexpr int kStages = 3;
-constexpr int kStageEntries = 4096;                   // payload entries staged per flush round
+constexpr int kWarpEntries = 256;                     // payload entries a warp stages per flush round
 
 enum StatusBits : unsigned { kStatusCapacity = 1u, kStatusWatchdog = 2u };
 
@@ -81,24 +83,28 @@ struct StreamParams {
 
 // dynamic shared memory layout (bytes)
 struct SmemLayout {
+    static constexpr int kXsWords = kWarpEntries + 4;                      // + alignment shift
+    static constexpr int kSdBytes = kWarpEntries + 16;
     static constexpr int stage = 0;                                        // kStages * kStageBytes
-    static constexpr int sxs = kStages * kStageBytes;                      // (kStageEntries + 4) ints
-    static constexpr int sd = sxs + (kStageEntries + 4) * 4;               // kStageEntries + 16 bytes
-    static constexpr int lut = sd + kStageEntries + 16;                    // 768 words
+    static constexpr int sxs = kStages * kStageBytes;                      // kWarps * kXsWords ints
+    static constexpr int sd = sxs + kWarps * kXsWords * 4;                 // kWarps * kSdBytes bytes
+    static constexpr int lut = sd + kWarps * kSdBytes;                     // 768 words
     static constexpr int hist = lut + 768 * 4;                             // 256 words
     static constexpr int wtot = hist + 256 * 4;                            // 2 x kWarps words (by step parity)
     static constexpr int red = wtot + 2 * kWarps * 4;                      // 2 x kWarps words
-    static constexpr int bar = red + 2 * kWarps * 4;                       // kStages mbarriers
+    static constexpr int done = red + 2 * kWarps * 4;                      // kStages words (+1 pad)
+    static constexpr int bar = done + (kStages + 1) * 4;                   // kStages mbarriers
     static constexpr int total = bar + kStages * 8;
 };
 static_assert(SmemLayout::bar % 8 == 0, "mbarrier alignment");
 static_assert(SmemLayout::sd % 16 == 0 && SmemLayout::sxs % 16 == 0, "staging alignment");
+static_assert((SmemLayout::kXsWords * 4) % 16 == 0 && SmemLayout::kSdBytes % 16 == 0, "per-warp staging alignment");
 
-// Coalesced flush of n staged entries to global rank g0.  The staging arrays were filled starting
-// at element (g0 & 3), so that 16-byte vectors of xs (and 4-byte words of diff) line up between
-// shared and global memory.
-__device__ __forceinline__ void flush_payload(const int *sxs, const uint8_t *sd, int *xs_out, uint8_t *df_out,
-                                              size_t g0, uint32_t n, size_t cap, uint32_t tid)
+// Coalesced flush by one warp of n staged entries to global rank g0.  The staging arrays were filled
+// starting at element (g0 & 3), so that 16-byte vectors of xs (and 4-byte words of diff) line up
+// between shared and global memory.
+__device__ __forceinline__ void flush_warp(const int *sxs, const uint8_t *sd, int *xs_out, uint8_t *df_out, size_t g0,
+                                           uint32_t n, size_t cap, uint32_t lane)
 {
     if (g0 >= cap) return;
     if (g0 + n > cap) n = (uint32_t)(cap - g0);
@@ -107,31 +113,19 @@ __device__ __forceinline__ void flush_payload(const int *sxs, const uint8_t *sd,
     int *xg = xs_out + (g0 - sh);
     uint8_t *dg = df_out + (g0 - sh);
     const uint32_t end = sh + n;
-    const uint32_t body0 = sh ? 4u : 0u;      // first fully valid quad
-    const uint32_t body1 = end & ~3u;         // end of the last fully valid quad
-    if (body1 > body0) {
-        const uint32_t nq = (body1 - body0) >> 2;
-        for (uint32_t q = tid; q < nq; q += kThreads) {
-            const uint32_t e = body0 + 4 * q;
+    // quads [4i, 4i+4): full ones go out as one 16-byte + one 4-byte store, the (at most two) partial ones
+    // at the ends element by element
+    for (uint32_t e = 4 * lane; e < end; e += 128) {
+        if (e >= sh && e + 4 <= end) {
             stg_stream(xg + e, *reinterpret_cast<const uint4 *>(sxs + e));
             stg_stream_u32(dg + e, *reinterpret_cast<const uint32_t *>(sd + e));
-        }
-    }
-    // head [sh, min(4,end)) and tail [max(body1,body0), end): at most 3 + 3 entries
-    if (tid < 8) {
-        uint32_t e;
-        bool ok;
-        if (tid < 4) {
-            e = tid;
-            ok = sh && e >= sh && e < end && e < 4u;
         } else {
-            e = (body1 > body0 ? body1 : body0) + (tid - 4);
-            ok = e < end && e >= sh && (body1 >= body0);
-            if (sh && body1 < 4u) ok = false; // everything sits in the head quad, already written
-        }
-        if (ok) {
-            stg_stream_u32(xg + e, (uint32_t)sxs[e]);
-            stg_stream_u8(dg + e, sd[e]);
+#pragma unroll
+            for (uint32_t i = 0; i < 4; i++)
+                if (e + i >= sh && e + i < end) {
+                    stg_stream_u32(xg + e + i, (uint32_t)sxs[e + i]);
+                    stg_stream_u8(dg + e + i, sd[e + i]);
+                }
         }
     }
 }
@@ -159,12 +153,11 @@ template <int MODE, bool HI, bool REFREG>
 __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    int *sxs = reinterpret_cast<int *>(smem + SmemLayout::sxs);
-    uint8_t *sd = smem + SmemLayout::sd;
     uint32_t *slut = reinterpret_cast<uint32_t *>(smem + SmemLayout::lut);
     uint32_t *shist = reinterpret_cast<uint32_t *>(smem + SmemLayout::hist);
     uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + SmemLayout::wtot);
     uint32_t *red = reinterpret_cast<uint32_t *>(smem + SmemLayout::red);
+    uint32_t *done = reinterpret_cast<uint32_t *>(smem + SmemLayout::done);
     const uint32_t stage_addr = smem_u32(smem + SmemLayout::stage);
     const uint32_t bar_addr = smem_u32(smem + SmemLayout::bar);
 
@@ -174,6 +167,9 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
     const uint32_t nsteps = (uint32_t)p.nframes * p.nseg;
     constexpr bool kBinarize = (MODE == kModeBinarize || MODE == kModeBinarizeAvg);
     constexpr bool kGrayW = (MODE == kModeGrayWeighted || MODE == kModeBinarize);
+    // this warp's staging window
+    int *sxs = reinterpret_cast<int *>(smem + SmemLayout::sxs) + warp * SmemLayout::kXsWords;
+    uint8_t *sd = smem + SmemLayout::sd + warp * SmemLayout::kSdBytes;
 
     uint32_t phase = 0;     // bit st: parity the next wait on stage st expects
     bool tripped = false;   // watchdog expired once: stop waiting altogether
@@ -188,12 +184,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
         off = (uint32_t)o;
         bytes = (uint32_t)(e - o);
     };
-    uint64_t pol = 0;
-    auto issue = [&](uint32_t q) { // thread 0 only
+    // one thread: refill the ring stage of step q
+    auto issue = [&](uint32_t q) {
         uint32_t t = q / p.nseg, s = q - t * p.nseg, off, bytes;
         slice(s, off, bytes);
         if (bytes) {
             const uint32_t st = q % kStages;
+            const uint64_t pol = l2_policy_evict_first();
             // the stage was last written through the generic proxy (parked difference bytes)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar_addr + 8 * st, bytes);
@@ -204,16 +201,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < kStages; i++) mbar_init(bar_addr + 8 * i, 1);
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(bar_addr + 8 * i, 1);
+            done[i] = 0;
+        }
         mbar_init_fence();
     }
     if (MODE == kModeHeat)
         for (uint32_t i = tid; i < 766; i += kThreads) slut[i] = p.heat_lut[i];
     __syncthreads();
-    if (tid == 0) {
-        pol = l2_policy_evict_first();
+    if (tid == 0)
         for (uint32_t q = 0; q < (uint32_t)kStages && q < nsteps; q++) issue(q);
-    }
 
     uint32_t r[kGroupWords];
     const uint64_t keep = l2_policy_evict_last();
@@ -250,11 +248,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
     // The loop is software-pipelined by one step: iteration q runs the FRONT half of step q (ingest, flags,
     // change mask, feedback, counts, publish) and then the BACK half of step q-1 (look-back sum, staging,
     // flush).  The predecessors' descriptors of step q-1 are fetched at the top of the iteration, so their L2
-    // round trip hides behind the front half, and one barrier serves both the block scan of step q and the
-    // look-back reduction of step q-1.
-    uint32_t b_lo = 0, b_hi = 0, b_lrank = 0, b_total = 0, b_goff = 0, b_myaddr = 0, b_t = 0, b_s = 0;
+    // round trip hides behind the front half, and the single barrier of an iteration serves both the block
+    // scan of step q and the look-back reduction of step q-1.
+    uint32_t b_lo = 0, b_hi = 0, b_lrank = 0, b_wexc = 0, b_wtotal = 0, b_total = 0, b_goff = 0, b_myaddr = 0;
+    uint32_t b_t = 0, b_s = 0;
     bool pending = false;
     uint32_t t = 0, s = 0; // frame and segment of step q
+    // number of warps of this block that hold groups (the others never stage anything but still count as done)
 
     for (uint32_t q = 0; q <= nsteps; q++) {
         const bool front = q < nsteps;
@@ -407,17 +407,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
             if (lane == 0) red[(q & 1u) * kWarps + warp] = part;
         }
 
-        __syncthreads(); // S1: warp totals of step q and look-back partial sums of step q-1
+        __syncthreads(); // the one barrier of a step: warp totals of step q, look-back partial sums of step q-1
 
-        uint32_t total = 0, lrank = 0;
+        uint32_t total = 0, lrank = 0, wexc = 0;
         if (front) {
             uint32_t wv = lane < (uint32_t)kWarps ? wtot[(q & 1u) * kWarps + lane] : 0u;
             uint32_t winc = warp_incl_scan(wv, lane);
             total = __shfl_sync(0xffffffffu, winc, kWarps - 1);
-            const uint32_t wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
+            wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
             lrank = wexc + incl - cnt; // rank of this thread's first entry inside the block
             if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
         }
+        const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
 
         if (pending) {
             uint32_t base;
@@ -433,18 +434,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 if ((size_t)base + b_total > p.cap) atomicOr(p.status, kStatusCapacity);
             }
 
-            // ---- stage (index, value) of step q-1 in rank order and flush; rounds of kStageEntries
+            // ---- this warp stages the (index, value) entries of its lanes for step q-1 in rank order and
+            //      flushes them, kWarpEntries at a time; no other warp is involved
             int *xs_out = p.xs + (size_t)b_t * p.cap;
             uint8_t *df_out = p.diff + (size_t)b_t * p.cap;
             const uint32_t b_cnt = (uint32_t)__popc(b_lo) + (uint32_t)__popc(b_hi);
-            for (uint32_t w0 = 0; w0 < ((p.debug & 2u) ? 0u : b_total); w0 += kStageEntries) {
-                const uint32_t wn = min(b_total - w0, (uint32_t)kStageEntries);
-                const size_t g0 = (size_t)base + w0;
+            const uint32_t wrank = b_lrank - b_wexc; // rank of this lane's first entry inside the warp
+            for (uint32_t w0 = 0; w0 < ((p.debug & 2u) ? 0u : b_wtotal); w0 += kWarpEntries) {
+                const uint32_t wn = min(b_wtotal - w0, (uint32_t)kWarpEntries);
+                const size_t g0 = (size_t)base + b_wexc + w0;
                 const uint32_t sh = (uint32_t)(g0 & 3);
-                if (w0) __syncthreads(); // previous round flushed
-                if (b_cnt && b_lrank < w0 + wn && b_lrank + b_cnt > w0) {
-                    uint32_t o = b_lrank - w0 + sh; // wraps below zero for a thread that straddles the window start
-                    if (b_lrank >= w0 && b_lrank + b_cnt <= w0 + wn) {
+                if (w0) __syncwarp(); // previous round flushed
+                if (b_cnt && wrank < w0 + wn && wrank + b_cnt > w0) {
+                    uint32_t o = wrank - w0 + sh; // wraps below zero for a lane that straddles the window start
+                    if (wrank >= w0 && wrank + b_cnt <= w0 + wn) {
                         emit_bits<false>(b_lo, 0, b_goff, b_myaddr, sxs, sd, o, sh, wn);
                         emit_bits<false>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
                     } else {
@@ -452,12 +455,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                         emit_bits<true>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
                     }
                 }
-                __syncthreads(); // S2
-                flush_payload(sxs, sd, xs_out, df_out, g0, wn, p.cap, tid);
+                __syncwarp();
+                flush_warp(sxs, sd, xs_out, df_out, g0, wn, p.cap, lane);
             }
-            // the stage of step q-1 is drained: every thread consumed its pixels before S1 of that step and
-            // emitted its parked bytes before the last S2 (none were parked when the total was 0): refill it
-            if (tid == 0 && q - 1 + kStages < nsteps) issue(q - 1 + kStages);
+            // ---- this warp is done with the ring stage of step q-1 (pixels consumed before the barrier of
+            //      that step, parked bytes emitted above); the last warp to get here refills the stage
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t stq = (q - 1) % kStages;
+                __threadfence_block();
+                if (atomicAdd(&done[stq], 1u) == (uint32_t)kWarps - 1u) {
+                    done[stq] = 0;
+                    if (q - 1 + kStages < nsteps) issue(q - 1 + kStages);
+                }
+            }
         }
 
         if (front) {
@@ -466,7 +477,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 for (uint32_t i = tid; i < 256; i += kThreads)
                     if (shist[i]) atomicAdd(p.hist + (size_t)t * 256 + i, shist[i]);
             }
-            b_lo = lo; b_hi = hi; b_lrank = lrank; b_total = total; b_goff = goff; b_myaddr = myaddr; b_t = t; b_s = s;
+            b_lo = lo; b_hi = hi; b_lrank = lrank; b_wexc = wexc; b_wtotal = wtotal; b_total = total;
+            b_goff = goff; b_myaddr = myaddr; b_t = t; b_s = s;
             pending = true;
             if (++s == p.nseg) { s = 0; ++t; }
         } else {
