@@ -146,7 +146,7 @@ StreamKernel pick_kernel(int mode, bool hi, bool refreg)
 struct cvs_stream_s {
     int width = 0, height = 0, threshold = 20, mode = 0, noise_filter = 0, ksize = 3, device = 0;
     int max_sequence = 512;
-    uint32_t N = 0, N16 = 0, ngroups = 0, npix = 0;
+    uint32_t N = 0, N16 = 0, nchunks = 0, npix = 0;
     size_t Npad = 0, P16 = 0;
     bool hi = false;
     uint32_t addc = 0;
@@ -310,10 +310,10 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 
     // ---- geometry of the persistent launch
     int G = 2 * h->sms;
-    if (G > cvs::kThreads) G = cvs::kThreads;
-    if ((uint32_t)G > h->ngroups) G = (int)h->ngroups;
-    uint32_t nseg = (uint32_t)((h->ngroups + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
-    uint32_t gps = (uint32_t)((h->ngroups + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+    if (G > 2 * cvs::kThreads) G = 2 * cvs::kThreads; // the look-back reads two predecessors per thread
+    if ((uint32_t)G > h->nchunks) G = (int)h->nchunks;
+    uint32_t nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+    uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
     StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cvs::SmemLayout::total));
@@ -322,8 +322,8 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
     if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
         G = occ * h->sms;
-        nseg = (uint32_t)((h->ngroups + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
-        gps = (uint32_t)((h->ngroups + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+        nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+        cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
         if ((nseg == 1) != refreg) return fail(CVS_ERR_INTERNAL, "occupancy changed the segment count");
     }
 
@@ -345,9 +345,9 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.ref = h->d_ref;
         p.nbytes = h->N;
         p.nbytes16 = h->N16;
-        p.ngroups = h->ngroups;
+        p.nchunks = h->nchunks;
         p.nseg = nseg;
-        p.gps = gps;
+        p.cps = cps;
         p.pos = d_pos + done;
         p.xs = d_xs + (size_t)done * cap;
         p.diff = d_diff + (size_t)done * cap;
@@ -461,8 +461,8 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     h->npix = (uint32_t)cfg->width * (uint32_t)cfg->height;
     h->N = 3u * h->npix;
     h->N16 = (uint32_t)round_up(h->N, 16);
-    h->ngroups = (h->N + cvs::kGroupBytes - 1) / cvs::kGroupBytes;
-    h->Npad = (size_t)h->ngroups * cvs::kGroupBytes;
+    h->nchunks = (h->N + cvs::kChunkBytes - 1) / cvs::kChunkBytes;
+    h->Npad = (size_t)h->nchunks * cvs::kChunkBytes;
     h->P16 = round_up(h->npix, 16);
     threshold_consts(cfg->threshold, h->hi, h->addc);
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);

@@ -6,24 +6,29 @@
 // 243-281).  nframes = 1 is the drop-in exec_core path; nframes = T walks a device-resident
 // sequence (frame t+1 is differenced against the reference frame t left behind).
 //
+// The path is integer byte work: on B200 it is bound by instruction issue long before HBM, so the
+// design minimises instructions per frame byte and keeps HBM traffic at its floor.
+//
 // Work decomposition
-//   * a frame is cut into groups of 48 B = 16 BGR pixels = three 16-byte vectors (cvs_pixel.cuh);
-//   * the grid is G persistent blocks of 512 threads, all co-resident (cooperative launch).  A frame
-//     is covered in nseg passes ("segments") of G*gps groups; in segment s block b owns the gps
-//     consecutive groups starting at (s*G + b)*gps and thread i of the block owns group i of that
+//   * a frame is cut into groups of 48 B = 16 BGR pixels = three 16-byte vectors (cvs_pixel.cuh); a
+//     thread owns a CHUNK of two consecutive groups (96 B), which halves the per-byte cost of the
+//     scans, the barrier, the look-back and the flush;
+//   * the grid is G persistent blocks of 256 threads, two per SM, all co-resident (cooperative launch).
+//     A frame is covered in nseg passes ("segments") of G*cps chunks; in segment s block b owns the cps
+//     consecutive chunks starting at (s*G + b)*cps and thread i of the block owns chunk i of that
 //     slice -- the SAME bytes in every frame.  One (frame, segment) pair is a "step";
 //   * ingest: a block streams its slice of the coming steps into a 3-stage shared-memory ring with
 //     1-D bulk copies (TMA engine, cp.async.bulk + mbarrier, L2 evict-first): every byte of a frame
-//     crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each thread picks its 16
-//     whole pixels out of shared memory with three conflict-free LDS.128;
-//   * reference: when a frame fits one segment (1080p on 148 SMs) the thread's 48 reference bytes
+//     crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each thread picks its 32
+//     whole pixels out of shared memory with six LDS.128;
+//   * reference: when a frame fits one segment (1080p on 148 SMs) the thread's 96 reference bytes
 //     live in registers for the whole sequence (REFREG): HBM never sees the reference between the
-//     first frame and the last.  Otherwise each thread reloads / rewrites its own 48 bytes with
-//     L2 evict-last accesses (the reference frame stays L2 resident; same thread, same address, so
-//     no cross-thread hazard exists);
-//   * one pass over the 12 words of a group produces, per word: byte-SIMD |cur-ref| > T flags, the
-//     4-bit change nibble (one multiply gathers the four flag bits) merged into a 48-bit change mask,
-//     the difference bytes cur-ref (parked in the thread's own 48 bytes of the ring stage) and the
+//     first frame and the last.  Otherwise each thread reloads / rewrites its own bytes with L2
+//     evict-last accesses (the reference frame stays L2 resident; same thread, same address, so no
+//     cross-thread hazard exists);
+//   * one pass over the 24 words of a chunk produces, per word: byte-SIMD |cur-ref| > T flags, the
+//     4-bit change nibble (one multiply gathers the four flag bits) merged into a 96-bit change mask,
+//     the difference bytes cur-ref (parked in the thread's own 96 bytes of the ring stage) and the
 //     updated reference (negative feedback).  popc of the mask is the thread's entry count;
 //   * compaction: warp shuffle scan + one block scan (the only block-wide barrier of a step);
 //     cross-block offsets by a one-round decoupled look-back: each block publishes
@@ -36,8 +41,7 @@
 //     same registers and written with 16-byte streaming stores;
 //   * the step loop is software-pipelined: while a block runs the front half of step q (ingest ...
 //     publish) the descriptors it needs for step q-1 are already in flight, and the back half of
-//     step q-1 (staging and flush) follows, so neither the L2 round trip of the look-back nor a late
-//     predecessor stalls it.
+//     step q-1 (staging and flush) follows, so the L2 round trip of the look-back stays hidden.
 //
 // Order, values and the new reference are bit-exact with oracle/cvs_oracle.c orc_diff_compact;
 // unlike kernel2 the payload order is deterministic (ascending byte index).
@@ -46,11 +50,15 @@
 
 namespace cvs {
 
-constexpr int kThreads = 512;                         // threads per block
+constexpr int kThreads = 256;                         // threads per block
 constexpr int kWarps = kThreads / 32;
-constexpr int kStageBytes = kThreads * kGroupBytes;   // 24,576 B: one block slice
+constexpr int kGroupsPerThread = 2;
+constexpr int kChunkBytes = kGroupsPerThread * kGroupBytes;   // 96
+constexpr int kChunkWords = kChunkBytes / 4;                  // 24
+constexpr int kMaskWords = kChunkBytes / 32;                  // 3
+constexpr int kStageBytes = kThreads * kChunkBytes;   // 24,576 B: one block slice
 constexpr int kStages = 3;
-constexpr int kWarpEntries = 256;                     // payload entries a warp stages per flush round
+constexpr int kWarpEntries = 512;                     // payload entries a warp stages per flush round
 
 enum StatusBits : unsigned { kStatusCapacity = 1u, kStatusWatchdog = 2u };
 
@@ -58,12 +66,12 @@ struct StreamParams {
     const uint8_t *frames;      // frame t at frames + t*frame_stride (16-byte aligned)
     size_t frame_stride;        // multiple of 16, >= nbytes rounded up to 16
     int nframes;
-    uint8_t *ref;               // reference frame, padded to ngroups*48 bytes
+    uint8_t *ref;               // reference frame, padded to a whole number of chunks
     uint32_t nbytes;            // N = 3*W*H
     uint32_t nbytes16;          // N rounded up to 16
-    uint32_t ngroups;           // ceil(N / 48)
+    uint32_t nchunks;           // ceil(N / 96)
     uint32_t nseg;              // segments per frame
-    uint32_t gps;               // groups per block per segment (<= kThreads)
+    uint32_t cps;               // chunks per block per segment (<= kThreads)
     unsigned int *pos;          // [nframes]
     int *xs;                    // frame t at xs + t*cap
     uint8_t *diff;              // frame t at diff + t*cap
@@ -130,10 +138,10 @@ __device__ __forceinline__ void flush_warp(const int *sxs, const uint8_t *sd, in
     }
 }
 
-// walks the set bits of `bits` (bit j <-> byte `jbase + j` of the group): index goes to sxs, the
+// walks the set bits of `bits` (bit j <-> byte `jbase + j` of the chunk): index goes to sxs, the
 // difference byte is fetched from the thread's parked bytes at shared address dvaddr
 template <bool CHECKED>
-__device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_t goff, uint32_t dvaddr, int *sxs,
+__device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_t coff, uint32_t dvaddr, int *sxs,
                                           uint8_t *sd, uint32_t &o, uint32_t sh, uint32_t wn)
 {
     while (bits) {
@@ -142,12 +150,14 @@ __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_
         if (!CHECKED || o - sh < wn) {
             uint32_t v;
             asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(dvaddr + j));
-            sxs[o] = (int)(goff + j);
+            sxs[o] = (int)(coff + j);
             sd[o] = (uint8_t)v;
         }
         o++;
     }
 }
+
+__device__ __forceinline__ uint32_t warp_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
 template <int MODE, bool HI, bool REFREG>
 __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
@@ -176,10 +186,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
     // slice of this block in segment s: byte offset and byte count of the bulk copy
     auto slice = [&](uint32_t s, uint32_t &off, uint32_t &bytes) {
-        uint64_t g0 = ((uint64_t)s * G + b) * p.gps;
-        uint64_t o = g0 * kGroupBytes;
+        uint64_t c0 = ((uint64_t)s * G + b) * p.cps;
+        uint64_t o = c0 * kChunkBytes;
         if (o >= p.nbytes16) { off = 0; bytes = 0; return; }
-        uint64_t e = o + (uint64_t)p.gps * kGroupBytes;
+        uint64_t e = o + (uint64_t)p.cps * kChunkBytes;
         if (e > p.nbytes16) e = p.nbytes16;
         off = (uint32_t)o;
         bytes = (uint32_t)(e - o);
@@ -213,68 +223,68 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
     if (tid == 0)
         for (uint32_t q = 0; q < (uint32_t)kStages && q < nsteps; q++) issue(q);
 
-    uint32_t r[kGroupWords];
+    uint32_t r[kChunkWords];
     const uint64_t keep = l2_policy_evict_last();
     bool dirty = false;
-    uint32_t goff = 0, nv = 0; // byte offset of this thread's group in the frame, valid bytes
+    uint32_t coff = 0, nv = 0; // byte offset of this thread's chunk in the frame, valid bytes (0..96)
+    uint32_t sbytes = 0;       // bytes of the block's slice in the current segment
     auto geometry = [&](uint32_t s) {
-        uint64_t g = ((uint64_t)s * G + b) * p.gps + tid;
-        bool ok = tid < p.gps && g < p.ngroups;
-        goff = ok ? (uint32_t)(g * kGroupBytes) : 0u;
-        nv = ok ? min(N - goff, (uint32_t)kGroupBytes) : 0u;
+        uint32_t soff;
+        slice(s, soff, sbytes);
+        uint64_t c = ((uint64_t)s * G + b) * p.cps + tid;
+        bool ok = tid < p.cps && c < p.nchunks;
+        coff = ok ? (uint32_t)(c * kChunkBytes) : 0u;
+        nv = ok ? min(N - coff, (uint32_t)kChunkBytes) : 0u;
     };
     auto load_ref = [&]() {
         if (nv) {
-            uint4 a = ldg_keep(p.ref + goff, keep), bq = ldg_keep(p.ref + goff + 16, keep), cq = ldg_keep(p.ref + goff + 32, keep);
-            r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
-            r[4] = bq.x; r[5] = bq.y; r[6] = bq.z; r[7] = bq.w;
-            r[8] = cq.x; r[9] = cq.y; r[10] = cq.z; r[11] = cq.w;
+#pragma unroll
+            for (int v = 0; v < kChunkWords / 4; v++) {
+                uint4 a = ldg_keep(p.ref + coff + 16 * v, keep);
+                r[4 * v] = a.x; r[4 * v + 1] = a.y; r[4 * v + 2] = a.z; r[4 * v + 3] = a.w;
+            }
         } else {
 #pragma unroll
-            for (int k = 0; k < kGroupWords; k++) r[k] = 0;
+            for (int k = 0; k < kChunkWords; k++) r[k] = 0;
         }
     };
     auto store_ref = [&]() {
-        stg_keep(p.ref + goff, make_uint4(r[0], r[1], r[2], r[3]), keep);
-        stg_keep(p.ref + goff + 16, make_uint4(r[4], r[5], r[6], r[7]), keep);
-        stg_keep(p.ref + goff + 32, make_uint4(r[8], r[9], r[10], r[11]), keep);
+#pragma unroll
+        for (int v = 0; v < kChunkWords / 4; v++)
+            stg_keep(p.ref + coff + 16 * v, make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]), keep);
     };
 
-    if (REFREG) { // nseg == 1: the geometry never changes
-        geometry(0);
-        load_ref();
-    }
+    geometry(0);
+    if (REFREG) load_ref(); // nseg == 1: the geometry never changes and the reference stays in registers
 
     // The loop is software-pipelined by one step: iteration q runs the FRONT half of step q (ingest, flags,
     // change mask, feedback, counts, publish) and then the BACK half of step q-1 (look-back sum, staging,
     // flush).  The predecessors' descriptors of step q-1 are fetched at the top of the iteration, so their L2
     // round trip hides behind the front half, and the single barrier of an iteration serves both the block
     // scan of step q and the look-back reduction of step q-1.
-    uint32_t b_lo = 0, b_hi = 0, b_lrank = 0, b_wexc = 0, b_wtotal = 0, b_total = 0, b_goff = 0, b_myaddr = 0;
-    uint32_t b_t = 0, b_s = 0;
+    uint32_t b_m[kMaskWords] = {0, 0, 0};
+    uint32_t b_wrank = 0, b_wexc = 0, b_wtotal = 0, b_total = 0, b_coff = 0, b_myaddr = 0, b_t = 0, b_s = 0;
     bool pending = false;
     uint32_t t = 0, s = 0; // frame and segment of step q
-    // number of warps of this block that hold groups (the others never stage anything but still count as done)
 
     for (uint32_t q = 0; q <= nsteps; q++) {
         const bool front = q < nsteps;
 
-        // ---- back half, part 1: start fetching the look-back descriptors of step q-1.  Thread i < b reads
-        //      predecessor i; thread b reads the running total of the earlier segments of the frame
-        const unsigned long long *pd = nullptr;
-        unsigned long long pv = 0;
-        if (pending && !(p.debug & 1u)) {
-            const unsigned long long *prow = p.desc + (size_t)(q - 1) * (G + 1);
-            if (tid < b) pd = prow + tid;
-            else if (tid == b && b_s > 0) pd = prow - (G + 1) + G;
-            if (pd) pv = desc_peek(pd);
-        }
+        // ---- back half, part 1: start fetching the look-back descriptors of step q-1.  Thread i reads
+        //      predecessors i, i+256, ...; thread b%256 also reads the running total of the earlier segments
+        unsigned long long pv0 = 0, pv1 = 0, pv2 = 0;
+        const unsigned long long *prow = p.desc + (size_t)(q ? q - 1 : 0) * (G + 1);
+        const bool look = pending && !(p.debug & 1u);
+        const bool has0 = look && tid < b, has1 = look && tid + kThreads < b;
+        const bool has2 = look && b_s > 0 && tid == (b & (kThreads - 1));
+        if (has0) pv0 = desc_peek(prow + tid);
+        if (has1) pv1 = desc_peek(prow + tid + kThreads);
+        if (has2) pv2 = desc_peek(prow - 1); // slot G of the previous step
 
-        uint32_t lo = 0, hi = 0, cnt = 0, incl = 0, myaddr = 0;
+        uint32_t m[kMaskWords] = {0, 0, 0};
+        uint32_t cnt = 0, incl = 0, myaddr = 0;
         if (front) {
             const uint32_t st = q % kStages;
-            uint32_t soff, sbytes;
-            slice(s, soff, sbytes);
             if (!REFREG) {
                 geometry(s);
                 load_ref(); // L2 hit; issued before the wait on the frame slice
@@ -286,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 __syncthreads();
             }
 
-            // ---- 1. this thread's 16 pixels out of the ring
+            // ---- 1. this thread's 32 pixels out of the ring
             if (sbytes) {
                 // steps with an empty slice never touch the barrier, so the parity is tracked per stage
                 if (!tripped && !mbar_wait(bar_addr + 8 * st, (phase >> st) & 1u)) {
@@ -295,16 +305,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 }
                 phase ^= 1u << st;
             }
-            myaddr = stage_addr + st * kStageBytes + tid * kGroupBytes;
-            uint32_t c[kGroupWords];
+            myaddr = stage_addr + st * kStageBytes + tid * kChunkBytes;
+            uint32_t c[kChunkWords];
             if (nv) {
-                uint4 x = lds128(myaddr), y = lds128(myaddr + 16), z = lds128(myaddr + 32);
-                c[0] = x.x; c[1] = x.y; c[2] = x.z; c[3] = x.w;
-                c[4] = y.x; c[5] = y.y; c[6] = y.z; c[7] = y.w;
-                c[8] = z.x; c[9] = z.y; c[10] = z.z; c[11] = z.w;
-                if (nv < (uint32_t)kGroupBytes) { // the group that holds the end of the frame: bytes past N never differ
 #pragma unroll
-                    for (int k = 0; k < kGroupWords; k++) {
+                for (int v = 0; v < kChunkWords / 4; v++) {
+                    uint4 x = lds128(myaddr + 16 * v);
+                    c[4 * v] = x.x; c[4 * v + 1] = x.y; c[4 * v + 2] = x.z; c[4 * v + 3] = x.w;
+                }
+                if (nv < (uint32_t)kChunkBytes) { // the chunk that holds the end of the frame: bytes past N never differ
+#pragma unroll
+                    for (int k = 0; k < kChunkWords; k++) {
                         const int vb = (int)nv - 4 * k;
                         const uint32_t vm = vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << (8 * vb)) - 1u));
                         c[k] = (c[k] & vm) | (r[k] & ~vm);
@@ -312,73 +323,85 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < kGroupWords; k++) c[k] = r[k];
+                for (int k = 0; k < kChunkWords; k++) c[k] = r[k];
             }
 
             // ---- 2. display filter on the same registers (reference as it was BEFORE this frame)
             if (MODE != kModeNone && nv) {
-                uint32_t o[kGroupWords];
-                if (MODE == kModeHeat) {
-                    uint32_t ad[kGroupWords];
 #pragma unroll
-                    for (int k = 0; k < kGroupWords; k++) ad[k] = absdiff4(c[k], r[k]);
-                    group_heat(ad, slut, o);
-                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
-                } else if (MODE == kModeRedBlack || MODE == kModeRedOverlap) {
-                    uint32_t mk[kGroupWords];
+                for (int g = 0; g < kGroupsPerThread; g++) {
+                    const uint32_t goff = coff + g * kGroupBytes;
+                    const uint32_t gnv = nv > (uint32_t)(g * kGroupBytes) ? min(nv - g * kGroupBytes, (uint32_t)kGroupBytes) : 0u;
+                    if (gnv == 0) continue;
+                    uint32_t cg[kGroupWords], rg[kGroupWords], o[kGroupWords];
 #pragma unroll
-                    for (int k = 0; k < kGroupWords; k++) mk[k] = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
-                    group_red<MODE == kModeRedOverlap>(mk, r, o);
-                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
-                } else if (MODE == kModeGrayWeighted || MODE == kModeGrayAverage) {
-                    group_gray3<kGrayW>(c, o);
-                    store_group(p.show + (size_t)t * p.show_stride + goff, o, nv);
-                } else if (kBinarize) {
-                    uint32_t g4[4];
-                    group_gray1<kGrayW>(c, g4);
-                    const uint32_t npx = nv / 3u; // whole pixels of this group inside the frame
-                    uint8_t *gdst = p.gray1 + (size_t)t * p.gray_stride + goff / 3u;
-                    if (npx == (uint32_t)kGroupPixels) stg_keep(gdst, make_uint4(g4[0], g4[1], g4[2], g4[3]), keep);
+                    for (int k = 0; k < kGroupWords; k++) { cg[k] = c[g * kGroupWords + k]; rg[k] = r[g * kGroupWords + k]; }
+                    if (MODE == kModeHeat) {
+                        uint32_t ad[kGroupWords];
 #pragma unroll
-                    for (int px = 0; px < kGroupPixels; px++) {
-                        if ((uint32_t)px < npx) {
-                            uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
-                            if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
-                            atomicAdd(&shist[gv], 1u); // server.cpp:103-106
+                        for (int k = 0; k < kGroupWords; k++) ad[k] = absdiff4(cg[k], rg[k]);
+                        group_heat(ad, slut, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (MODE == kModeRedBlack || MODE == kModeRedOverlap) {
+                        uint32_t mk[kGroupWords];
+#pragma unroll
+                        for (int k = 0; k < kGroupWords; k++) mk[k] = changed80<HI>(absdiff4(cg[k], rg[k]), p.addc);
+                        group_red<MODE == kModeRedOverlap>(mk, rg, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (MODE == kModeGrayWeighted || MODE == kModeGrayAverage) {
+                        group_gray3<kGrayW>(cg, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (kBinarize) {
+                        uint32_t g4[4];
+                        group_gray1<kGrayW>(cg, g4);
+                        const uint32_t npx = gnv / 3u; // whole pixels of this group inside the frame
+                        uint8_t *gdst = p.gray1 + (size_t)t * p.gray_stride + goff / 3u;
+                        if (npx == (uint32_t)kGroupPixels) stg_keep(gdst, make_uint4(g4[0], g4[1], g4[2], g4[3]), keep);
+#pragma unroll
+                        for (int px = 0; px < kGroupPixels; px++) {
+                            if ((uint32_t)px < npx) {
+                                uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                                if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
+                                atomicAdd(&shist[gv], 1u); // server.cpp:103-106
+                            }
                         }
                     }
                 }
             }
 
-            // ---- 3. one pass: flags -> 48-bit change mask, difference bytes, negative feedback
+            // ---- 3. one pass: flags -> 96-bit change mask, difference bytes, negative feedback
             //         reference := changed ? current : reference                      (test.cu:565-570)
             {
-                uint32_t dv[kGroupWords];
+                uint32_t dv[kChunkWords];
 #pragma unroll
-                for (int k = 0; k < kGroupWords; k++) {
-                    const uint32_t m = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
+                for (int k = 0; k < kChunkWords; k++) {
+                    const uint32_t f = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
                     // flag bits 7,15,23,31 -> adjacent bits 28..31 (all partial products land on distinct bits)
-                    const uint32_t nib = m * 0x00204081u;
-                    if (k < 8) lo |= (nib >> (28 - 4 * k)) & (0xFu << (4 * k));
-                    else hi |= (nib >> (28 - 4 * (k - 8))) & (0xFu << (4 * (k - 8)));
+                    const uint32_t nib = f * 0x00204081u;
+                    m[k >> 3] |= (nib >> (28 - 4 * (k & 7))) & (0xFu << (4 * (k & 7)));
                     dv[k] = sub4(c[k], r[k]);
-                    const uint32_t fm = spread80(m);
+                    const uint32_t fm = spread80(f);
                     r[k] = (c[k] & fm) | (r[k] & ~fm);
                 }
-                if (nv < (uint32_t)kGroupBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
-                    lo &= nv >= 32u ? 0xffffffffu : ((1u << nv) - 1u);
-                    hi &= nv <= 32u ? 0u : ((1u << (nv - 32u)) - 1u);
+                if (nv < (uint32_t)kChunkBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
+#pragma unroll
+                    for (int w = 0; w < kMaskWords; w++) {
+                        const int vb = (int)nv - 32 * w;
+                        m[w] &= vb >= 32 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << vb) - 1u));
+                    }
                 }
-                if (lo | hi) {
-                    // park the difference bytes in this thread's own 48 bytes of the stage
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr), "r"(dv[0]), "r"(dv[1]), "r"(dv[2]), "r"(dv[3]) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 16), "r"(dv[4]), "r"(dv[5]), "r"(dv[6]), "r"(dv[7]) : "memory");
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 32), "r"(dv[8]), "r"(dv[9]), "r"(dv[10]), "r"(dv[11]) : "memory");
+                if (m[0] | m[1] | m[2]) {
+                    // park the difference bytes in this thread's own 96 bytes of the stage
+#pragma unroll
+                    for (int v = 0; v < kChunkWords / 4; v++)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 16 * v), "r"(dv[4 * v]),
+                                     "r"(dv[4 * v + 1]), "r"(dv[4 * v + 2]), "r"(dv[4 * v + 3])
+                                     : "memory");
                     if (REFREG) dirty = true;
                     else store_ref();
                 }
             }
-            cnt = (uint32_t)__popc(lo) + (uint32_t)__popc(hi);
+            cnt = (uint32_t)__popc(m[0]) + (uint32_t)__popc(m[1]) + (uint32_t)__popc(m[2]);
             incl = warp_incl_scan(cnt, lane);
             if (lane == 31) wtot[(q & 1u) * kWarps + warp] = incl;
         }
@@ -386,36 +409,38 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
         // ---- back half, part 2: the descriptors fetched at the top (retry in the rare case a predecessor
         //      had not published yet)
         if (pending) {
-            uint32_t part = 0;
-            if (pd) {
-                if ((uint32_t)(pv >> 32) != p.epoch) {
+            auto settle = [&](unsigned long long v, const unsigned long long *d) -> uint32_t {
+                if ((uint32_t)(v >> 32) != p.epoch) {
                     const uint64_t t0 = global_ns();
                     do {
-                        __nanosleep(40);
-                        pv = desc_peek(pd);
-                        if ((uint32_t)(pv >> 32) == p.epoch || tripped) break;
+                        __nanosleep(100);
+                        v = desc_peek(d);
+                        if ((uint32_t)(v >> 32) == p.epoch || tripped) break;
                         if (global_ns() - t0 > kWatchdogNs) {
                             tripped = true;
                             atomicOr(p.status, kStatusWatchdog);
                         }
                     } while (true);
                 }
-                part = (uint32_t)pv;
-            }
-            // G <= kThreads is enforced by the host, so one pass covers every predecessor
-            part = warp_sum(part);
+                return (uint32_t)v;
+            };
+            uint32_t part = 0;
+            if (has0) part += settle(pv0, prow + tid);
+            if (has1) part += settle(pv1, prow + tid + kThreads);
+            if (has2) part += settle(pv2, prow - 1);
+            // G <= 2 * kThreads is enforced by the host, so two reads per thread cover every predecessor
+            part = warp_add(part);
             if (lane == 0) red[(q & 1u) * kWarps + warp] = part;
         }
 
         __syncthreads(); // the one barrier of a step: warp totals of step q, look-back partial sums of step q-1
 
-        uint32_t total = 0, lrank = 0, wexc = 0;
+        uint32_t total = 0, wexc = 0;
         if (front) {
             uint32_t wv = lane < (uint32_t)kWarps ? wtot[(q & 1u) * kWarps + lane] : 0u;
             uint32_t winc = warp_incl_scan(wv, lane);
             total = __shfl_sync(0xffffffffu, winc, kWarps - 1);
-            wexc = __shfl_sync(0xffffffffu, winc - wv, warp);
-            lrank = wexc + incl - cnt; // rank of this thread's first entry inside the block
+            wexc = __shfl_sync(0xffffffffu, winc - wv, warp); // entries of the warps before this one
             if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
         }
         const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
             uint32_t base;
             {
                 uint32_t v = lane < (uint32_t)kWarps ? red[(q & 1u) * kWarps + lane] : 0u;
-                base = warp_sum(v);
+                base = warp_add(v);
             }
             if (tid == 0) {
                 if (b == G - 1) {
@@ -438,21 +463,20 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
             //      flushes them, kWarpEntries at a time; no other warp is involved
             int *xs_out = p.xs + (size_t)b_t * p.cap;
             uint8_t *df_out = p.diff + (size_t)b_t * p.cap;
-            const uint32_t b_cnt = (uint32_t)__popc(b_lo) + (uint32_t)__popc(b_hi);
-            const uint32_t wrank = b_lrank - b_wexc; // rank of this lane's first entry inside the warp
+            const uint32_t b_cnt = (uint32_t)__popc(b_m[0]) + (uint32_t)__popc(b_m[1]) + (uint32_t)__popc(b_m[2]);
             for (uint32_t w0 = 0; w0 < ((p.debug & 2u) ? 0u : b_wtotal); w0 += kWarpEntries) {
                 const uint32_t wn = min(b_wtotal - w0, (uint32_t)kWarpEntries);
                 const size_t g0 = (size_t)base + b_wexc + w0;
                 const uint32_t sh = (uint32_t)(g0 & 3);
                 if (w0) __syncwarp(); // previous round flushed
-                if (b_cnt && wrank < w0 + wn && wrank + b_cnt > w0) {
-                    uint32_t o = wrank - w0 + sh; // wraps below zero for a lane that straddles the window start
-                    if (wrank >= w0 && wrank + b_cnt <= w0 + wn) {
-                        emit_bits<false>(b_lo, 0, b_goff, b_myaddr, sxs, sd, o, sh, wn);
-                        emit_bits<false>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+                if (b_cnt && b_wrank < w0 + wn && b_wrank + b_cnt > w0) {
+                    uint32_t o = b_wrank - w0 + sh; // wraps below zero for a lane that straddles the window start
+                    if (b_wrank >= w0 && b_wrank + b_cnt <= w0 + wn) {
+#pragma unroll
+                        for (int w = 0; w < kMaskWords; w++) emit_bits<false>(b_m[w], 32 * w, b_coff, b_myaddr, sxs, sd, o, sh, wn);
                     } else {
-                        emit_bits<true>(b_lo, 0, b_goff, b_myaddr, sxs, sd, o, sh, wn);
-                        emit_bits<true>(b_hi, 32, b_goff, b_myaddr, sxs, sd, o, sh, wn);
+#pragma unroll
+                        for (int w = 0; w < kMaskWords; w++) emit_bits<true>(b_m[w], 32 * w, b_coff, b_myaddr, sxs, sd, o, sh, wn);
                     }
                 }
                 __syncwarp();
@@ -477,8 +501,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 for (uint32_t i = tid; i < 256; i += kThreads)
                     if (shist[i]) atomicAdd(p.hist + (size_t)t * 256 + i, shist[i]);
             }
-            b_lo = lo; b_hi = hi; b_lrank = lrank; b_wexc = wexc; b_wtotal = wtotal; b_total = total;
-            b_goff = goff; b_myaddr = myaddr; b_t = t; b_s = s;
+#pragma unroll
+            for (int w = 0; w < kMaskWords; w++) b_m[w] = m[w];
+            b_wrank = incl - cnt; b_wexc = wexc; b_wtotal = wtotal; b_total = total;
+            b_coff = coff; b_myaddr = myaddr; b_t = t; b_s = s;
             pending = true;
             if (++s == p.nseg) { s = 0; ++t; }
         } else {
