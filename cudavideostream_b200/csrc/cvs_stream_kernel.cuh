@@ -58,7 +58,8 @@ constexpr int kChunkWords = kChunkBytes / 4;                  // 24
 constexpr int kMaskWords = kChunkBytes / 32;                  // 3
 constexpr int kStageBytes = kThreads * kChunkBytes;   // 24,576 B: one block slice
 constexpr int kStages = 3;
-constexpr int kWarpEntries = 512;                     // payload entries a warp stages per flush round
+constexpr int kWarpEntries = 512;                     // payload entries a warp's staging window holds
+constexpr uint32_t kWatchdogPolls = 1u << 24;         // look-back polls (>= 100 ns each) before giving up
 
 enum StatusBits : unsigned { kStatusCapacity = 1u, kStatusWatchdog = 2u };
 
@@ -140,24 +141,69 @@ __device__ __forceinline__ void flush_warp(const int *sxs, const uint8_t *sd, in
 
 // walks the set bits of `bits` (bit j <-> byte `jbase + j` of the chunk): index goes to sxs, the
 // difference byte is fetched from the thread's parked bytes at shared address dvaddr
-template <bool CHECKED>
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_t coff, uint32_t dvaddr, int *sxs,
-                                          uint8_t *sd, uint32_t &o, uint32_t sh, uint32_t wn)
+                                          uint8_t *sd, uint32_t &o)
 {
     while (bits) {
         const uint32_t j = jbase + (uint32_t)__ffs((int)bits) - 1u;
         bits &= bits - 1u;
-        if (!CHECKED || o - sh < wn) {
-            uint32_t v;
-            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(dvaddr + j));
-            sxs[o] = (int)(coff + j);
-            sd[o] = (uint8_t)v;
-        }
+        sxs[o] = (int)(coff + j);
+        sd[o] = (uint8_t)lds_u8(dvaddr + j);
         o++;
     }
 }
 
+// Dense warps (more entries than the staging window holds): the warp walks its 32 chunks one after the other
+// and handles each chunk with all lanes -- lane L owns bytes L, L+32 and L+64 of the chunk, finds its rank by a
+// popc over the broadcast change mask and stores straight to global memory.  Consecutive changed bytes land on
+// consecutive ranks, so every store instruction writes one contiguous run (up to 128 B of indices).
+__device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
+                                          int *xs_out, uint8_t *df_out, uint32_t g_lane, size_t cap, uint32_t lane)
+{
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll 8
+    for (uint32_t S = 0; S < 32; S++) { // unrolled: the shuffles of several chunks overlap
+        const uint32_t s0 = __shfl_sync(0xffffffffu, m[0], S), s1 = __shfl_sync(0xffffffffu, m[1], S),
+                       s2 = __shfl_sync(0xffffffffu, m[2], S);
+        uint32_t r = __shfl_sync(0xffffffffu, g_lane, S); // global rank of the chunk's first entry
+        const uint32_t cb = coff0 + S * kChunkBytes + lane, da = dvaddr0 + S * kChunkBytes + lane;
+        const uint32_t sm[3] = {s0, s1, s2};
+#pragma unroll
+        for (int w = 0; w < kMaskWords; w++) {
+            if ((sm[w] >> lane) & 1u) {
+                const uint32_t g = r + (uint32_t)__popc(sm[w] & lt);
+                if (g < cap) {
+                    stg_stream_u32(xs_out + g, cb + 32 * w);
+                    stg_stream_u8(df_out + g, lds_u8(da + 32 * w));
+                }
+            }
+            r += (uint32_t)__popc(sm[w]);
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t warp_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// sum of the first n (<= 8) and of all 8 words at p (two broadcast 16-byte shared loads, no shuffles)
+__device__ __forceinline__ void sum8(const uint32_t *p, uint32_t n, uint32_t &first_n, uint32_t &all)
+{
+    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + 4);
+    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    first_n = 0; all = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if ((uint32_t)i < n) first_n += v[i];
+        all += v[i];
+    }
+}
+static_assert(kWarps == 8, "sum8 assumes eight warps per block");
 
 template <int MODE, bool HI, bool REFREG>
 __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
@@ -402,25 +448,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 }
             }
             cnt = (uint32_t)__popc(m[0]) + (uint32_t)__popc(m[1]) + (uint32_t)__popc(m[2]);
-            incl = warp_incl_scan(cnt, lane);
-            if (lane == 31) wtot[(q & 1u) * kWarps + warp] = incl;
+            // only the warp total has to cross the barrier; the per-lane ranks are scanned after it
+            const uint32_t wsum = warp_add(cnt);
+            if (lane == 0) wtot[(q & 1u) * kWarps + warp] = wsum;
         }
 
         // ---- back half, part 2: the descriptors fetched at the top (retry in the rare case a predecessor
         //      had not published yet)
         if (pending) {
             auto settle = [&](unsigned long long v, const unsigned long long *d) -> uint32_t {
-                if ((uint32_t)(v >> 32) != p.epoch) {
-                    const uint64_t t0 = global_ns();
-                    do {
-                        __nanosleep(100);
-                        v = desc_peek(d);
-                        if ((uint32_t)(v >> 32) == p.epoch || tripped) break;
-                        if (global_ns() - t0 > kWatchdogNs) {
-                            tripped = true;
-                            atomicOr(p.status, kStatusWatchdog);
-                        }
-                    } while (true);
+                uint32_t polls = 0;
+                while ((uint32_t)(v >> 32) != p.epoch && !tripped) {
+                    __nanosleep(64);
+                    v = desc_peek(d);
+                    if (++polls > kWatchdogPolls) { // each poll costs well over 100 ns: seconds, i.e. a bug
+                        tripped = true;
+                        atomicOr(p.status, kStatusWatchdog);
+                    }
                 }
                 return (uint32_t)v;
             };
@@ -435,22 +479,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
         __syncthreads(); // the one barrier of a step: warp totals of step q, look-back partial sums of step q-1
 
-        uint32_t total = 0, wexc = 0;
+        uint32_t total = 0, wexc = 0, wtotal = 0;
         if (front) {
-            uint32_t wv = lane < (uint32_t)kWarps ? wtot[(q & 1u) * kWarps + lane] : 0u;
-            uint32_t winc = warp_incl_scan(wv, lane);
-            total = __shfl_sync(0xffffffffu, winc, kWarps - 1);
-            wexc = __shfl_sync(0xffffffffu, winc - wv, warp); // entries of the warps before this one
+            sum8(wtot + (q & 1u) * kWarps, warp, wexc, total); // entries of the warps before this one / of the block
             if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
+            incl = warp_incl_scan(cnt, lane);
+            wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
         }
-        const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
 
         if (pending) {
-            uint32_t base;
-            {
-                uint32_t v = lane < (uint32_t)kWarps ? red[(q & 1u) * kWarps + lane] : 0u;
-                base = warp_add(v);
-            }
+            uint32_t base, unused;
+            sum8(red + (q & 1u) * kWarps, 0, unused, base);
             if (tid == 0) {
                 if (b == G - 1) {
                     desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
@@ -459,28 +498,25 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 if ((size_t)base + b_total > p.cap) atomicOr(p.status, kStatusCapacity);
             }
 
-            // ---- this warp stages the (index, value) entries of its lanes for step q-1 in rank order and
-            //      flushes them, kWarpEntries at a time; no other warp is involved
+            // ---- back half, part 3: the (index, value) entries of step q-1.  A warp whose entries fit its staging
+            //      window writes them there in rank order and flushes the window coalesced; a denser warp lets every
+            //      lane store its own run of entries directly.  No other warp is involved either way.
             int *xs_out = p.xs + (size_t)b_t * p.cap;
             uint8_t *df_out = p.diff + (size_t)b_t * p.cap;
-            const uint32_t b_cnt = (uint32_t)__popc(b_m[0]) + (uint32_t)__popc(b_m[1]) + (uint32_t)__popc(b_m[2]);
-            for (uint32_t w0 = 0; w0 < ((p.debug & 2u) ? 0u : b_wtotal); w0 += kWarpEntries) {
-                const uint32_t wn = min(b_wtotal - w0, (uint32_t)kWarpEntries);
-                const size_t g0 = (size_t)base + b_wexc + w0;
-                const uint32_t sh = (uint32_t)(g0 & 3);
-                if (w0) __syncwarp(); // previous round flushed
-                if (b_cnt && b_wrank < w0 + wn && b_wrank + b_cnt > w0) {
-                    uint32_t o = b_wrank - w0 + sh; // wraps below zero for a lane that straddles the window start
-                    if (b_wrank >= w0 && b_wrank + b_cnt <= w0 + wn) {
+            const size_t g0 = (size_t)base + b_wexc; // global rank of this warp's first entry
+            if (b_wtotal && !(p.debug & 2u)) {
+                if (b_wtotal <= (uint32_t)kWarpEntries) {
+                    uint32_t o = b_wrank + (uint32_t)(g0 & 3);
 #pragma unroll
-                        for (int w = 0; w < kMaskWords; w++) emit_bits<false>(b_m[w], 32 * w, b_coff, b_myaddr, sxs, sd, o, sh, wn);
-                    } else {
-#pragma unroll
-                        for (int w = 0; w < kMaskWords; w++) emit_bits<true>(b_m[w], 32 * w, b_coff, b_myaddr, sxs, sd, o, sh, wn);
-                    }
+                    for (int w = 0; w < kMaskWords; w++) emit_bits(b_m[w], 32 * w, b_coff, b_myaddr, sxs, sd, o);
+                    __syncwarp();
+                    flush_warp(sxs, sd, xs_out, df_out, g0, b_wtotal, p.cap, lane);
+                } else {
+                    // chunk S of the warp starts 96*S bytes after lane 0's chunk (frame and ring stage alike); lane 0 holds a
+                    // chunk of the frame whenever any lane of the warp does
+                    emit_coop(b_m, __shfl_sync(0xffffffffu, b_coff, 0), b_myaddr - lane * kChunkBytes, xs_out, df_out,
+                              (uint32_t)g0 + b_wrank, p.cap, lane);
                 }
-                __syncwarp();
-                flush_warp(sxs, sd, xs_out, df_out, g0, wn, p.cap, lane);
             }
             // ---- this warp is done with the ring stage of step q-1 (pixels consumed before the barrier of
             //      that step, parked bytes emitted above); the last warp to get here refills the stage
