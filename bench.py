@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.004)
 
     def result(self):
         self.stop_flag = True
@@ -245,16 +245,10 @@ def ours(args):
         tot_ms += mean_ms
     frames_done = args.steps * T * len(seqs)
 
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-        f = torch.tensor([frames_done, launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(f, op=dist.ReduceOp.SUM)
-        frames_total, launches_total = int(f[0].item()), int(f[1].item())
-    else:
-        frames_total, launches_total = frames_done, launches
-    value = frames_total / (elapsed_ms * 1e-3)
+    # whole-job view: max over ranks of the device time, sum over ranks of the work (no data-path collective)
+    elapsed_s, (frames_total, launches_total) = cvs.sharding.reduce_job(elapsed_ms * 1e-3, [frames_done, launches], dev)
+    elapsed_ms = elapsed_s * 1e3
+    value = frames_total / elapsed_s
 
     # ---- end to end through the drop-in call: frames in pinned host memory, pipelined submit/wait
     e2e = e2e_run(cvs, torch, dist, args, seqs, local, world, barrier)
@@ -349,14 +343,8 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     nfr = frames_per_density * len(rings)
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local))
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        f = torch.tensor([nfr, d2h], dtype=torch.int64, device=torch.device("cuda", local))
-        dist.all_reduce(f, op=dist.ReduceOp.SUM)
-        nfr, d2h = int(f[0].item()), int(f[1].item())
     launches = sum(q["stream"].launch_count() for q in rings) - launches0
+    dt, (nfr, d2h, launches) = cvs.sharding.reduce_job(dt, [nfr, d2h, launches], torch.device("cuda", local))
     tm = rings[1]["stream"].timing()
     res = {"value": nfr / dt, "unit": "frames/s", "h2d_bytes_per_step": N * nfr, "d2h_bytes_per_step": d2h,
            "frames": nfr, "seconds": dt, "gpu_launches": launches,
@@ -371,7 +359,7 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=SEQ_FRAMES, help="frames per sequence")

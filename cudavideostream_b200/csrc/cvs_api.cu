@@ -113,11 +113,25 @@ struct Slot {
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_pos = nullptr,
                 ev_p0 = nullptr, ev_done = nullptr;
     bool busy = false;
+    bool pushed = false; // payload already written to the caller's pinned buffers by k_payload_push
     uint64_t ticket = 0;
     uint8_t *u_frame = nullptr;
     int *u_xs = nullptr;
     unsigned int *u_pos = nullptr;
 };
+
+// true when `host` is pinned host memory the current device can write through `*dev`
+bool mapped_device_pointer(const void *host, void **dev)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return false;
+    *dev = attr.devicePointer;
+    return true;
+}
 
 typedef void (*StreamKernel)(const cvs::StreamParams);
 
@@ -580,9 +594,19 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp);
     if (st) return st;
     CU_TRY(cudaEventRecord(s.ev_k1, h->s_comp));
-    // D2H of the count (kernels.cu:507) and of the display frame
+    // D2H of the count (kernels.cu:507) and of the display frame.  When the caller's payload buffers are
+    // pinned (cvs_alloc_host) a copy kernel that reads the count on the device pushes exactly pos entries
+    // into them, so no host round trip separates the count from the payload (kernels.cu:507-508 + :522-524).
     CU_TRY(cudaStreamWaitEvent(h->s_d2h, s.ev_k1, 0));
     CU_TRY(cudaEventRecord(s.ev_p0, h->s_d2h));
+    void *dev_diff = nullptr, *dev_xs = nullptr;
+    s.pushed = mapped_device_pointer(diff_out, &dev_diff) && mapped_device_pointer(xs, &dev_xs) &&
+               ((uintptr_t)dev_diff % 16 == 0) && ((uintptr_t)dev_xs % 16 == 0);
+    if (s.pushed) {
+        cvs::k_payload_push<<<h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, (int *)dev_xs, (uint8_t *)dev_diff, cap);
+        CU_TRY(cudaGetLastError());
+        h->launches++;
+    }
     CU_TRY(cudaMemcpyAsync(s.h_pos, s.d_pos, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
     if (dshow) CU_TRY(cudaMemcpyAsync(show, dshow, h->N, cudaMemcpyDeviceToHost, h->s_d2h));
@@ -614,7 +638,7 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
     if (st == CVS_ERR_INTERNAL) return st;
     const unsigned int n = *s.h_pos;
     // payload (kernels.cu:522-523): diff bytes over the head of the frame buffer, then the indices
-    if (n) {
+    if (n && !s.pushed) {
         CU_TRY(cudaMemcpyAsync(s.u_frame, s.d_diff, n, cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(s.u_xs, s.d_xs, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
     }

@@ -281,6 +281,25 @@ __global__ void __launch_bounds__(256) k_client_apply(uint8_t *frame, const int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// egress: push exactly pos payload entries from the device buffers into the caller's pinned host buffers
+// (mapped into the device address space), 16 bytes per store.  Replaces the count round trip + two
+// cudaMemcpyAsync of server/src/kernels.cu:507-508, 522-524.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_payload_push(const int *__restrict__ xs, const uint8_t *__restrict__ diff,
+                                                      const unsigned int *__restrict__ pos, int *h_xs, uint8_t *h_diff,
+                                                      size_t capacity)
+{
+    size_t n = *pos;
+    if (n > capacity) n = capacity;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    const size_t xq = n / 4, dq = n / 16; // whole 16-byte vectors
+    for (size_t i = tid; i < xq; i += nt) reinterpret_cast<uint4 *>(h_xs)[i] = reinterpret_cast<const uint4 *>(xs)[i];
+    for (size_t i = tid; i < dq; i += nt) reinterpret_cast<uint4 *>(h_diff)[i] = reinterpret_cast<const uint4 *>(diff)[i];
+    for (size_t i = 4 * xq + tid; i < n; i += nt) h_xs[i] = xs[i];
+    for (size_t i = 16 * dq + tid; i < n; i += nt) h_diff[i] = diff[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic camera; numpy twin: cudavideostream_b200/synth.py
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint8_t synth_base_byte(uint64_t seed, uint32_t i, int width, int height)
