@@ -312,7 +312,7 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
             arr[t * N:(t + 1) * N] = src[(t + 1) * N:(t + 2) * N].cpu().numpy()
         base = src[:N].cpu().numpy()
         s = cvs.Stream(W, H, base, threshold=THR, device=local)
-        out = [(cvs.alloc_host(N + 32), cvs.alloc_host(4 * N + 32), (C.c_uint * 1)()) for _ in range(2)]
+        out = [(cvs.alloc_host(N + 32), cvs.alloc_host(4 * N + 32), (C.c_uint * 1)()) for _ in range(4)]
         rings.append({"hb": hb, "stream": s, "out": out})
     order = list(range(R)) + list(range(R - 2, 0, -1))
 
@@ -322,8 +322,8 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
             s, hb, out = q["stream"], q["hb"], q["out"]
             pending = []
             for i in range(nframes):
-                fb, xb, pb = out[i % 2]
-                if len(pending) == 2:
+                fb, xb, pb = out[i % 4]
+                if len(pending) == 4:
                     tk, pp = pending.pop(0)
                     s.wait(tk)
                     d2h += 4 + 5 * pp[0]

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 
@@ -103,6 +104,8 @@ int grid_for(size_t items, int block, int sms)
     return (int)blocks;
 }
 
+constexpr int kSlots = 4; // tickets that may be outstanding per stream
+
 struct Slot {
     uint8_t *d_in = nullptr;   // raw frame as uploaded
     int *d_xs = nullptr;
@@ -113,12 +116,20 @@ struct Slot {
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_pos = nullptr,
                 ev_p0 = nullptr, ev_done = nullptr;
     bool busy = false;
+    bool copied = false; // payload fetched with cudaMemcpyAsync in cvs_wait (ev_done is valid)
     bool pushed = false; // payload already written to the caller's pinned buffers by k_payload_push
     uint64_t ticket = 0;
     uint8_t *u_frame = nullptr;
     int *u_xs = nullptr;
     unsigned int *u_pos = nullptr;
 };
+
+double host_us()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
 
 // true when `host` is pinned host memory the current device can write through `*dev`
 bool mapped_device_pointer(const void *host, void **dev)
@@ -165,6 +176,9 @@ struct cvs_stream_s {
     bool hi = false;
     uint32_t addc = 0;
     uint32_t debug = 0; // CVS_DEBUG_FLAGS (profiling experiments only)
+    bool trace = false;
+    cudaEvent_t ev_base = nullptr;
+    bool push_payload = true; // CVS_PAYLOAD_PUSH=0 falls back to count round trip + copy engine
     cvs::ConvWeights weights;
     int sms = 0;
     // glyph atlas
@@ -187,8 +201,10 @@ struct cvs_stream_s {
     int *d_thr = nullptr;
     size_t bin_frames = 0;
     // geometry of the persistent launch (per kernel variant)
-    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    Slot slot[2];
+    cudaStream_t s_comp = nullptr, s_h2d = nullptr, s_d2h = nullptr, s_pay = nullptr;
+    Slot slot[kSlots];
+    int last_slot = -1; // slot of the most recently completed ticket (for cvs_get_timing)
+    int occ_cache[8][2][2] = {}; // co-resident blocks per SM of each k_stream variant (0 = not queried yet)
     uint64_t next_ticket = 1;
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
@@ -330,9 +346,11 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
     StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cvs::SmemLayout::total));
-    int occ = 0;
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, cvs::SmemLayout::total));
+    int &occ = h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
+    if (occ == 0) { // first launch of this variant on this handle
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cvs::SmemLayout::total));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, cvs::SmemLayout::total));
+    }
     if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
     if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
         G = occ * h->sms;
@@ -398,7 +416,8 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 cvs_status check_handle(cvs_handle h)
 {
     if (!h) return fail(CVS_ERR_INVALID, "null handle");
-    CU_TRY(cudaSetDevice(h->device));
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != h->device) CU_TRY(cudaSetDevice(h->device));
     return CVS_OK;
 }
 
@@ -480,6 +499,8 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     h->P16 = round_up(h->npix, 16);
     threshold_consts(cfg->threshold, h->hi, h->addc);
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
+    if (const char *pp = getenv("CVS_PAYLOAD_PUSH")) h->push_payload = atoi(pp) != 0;
+    if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
     CU_TRY(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -487,6 +508,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     CU_TRY(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->s_pay, cudaStreamNonBlocking));
     CU_TRY(cudaMalloc(&h->d_ref, h->Npad + 64));
     CU_TRY(cudaMemset(h->d_ref, 0, h->Npad + 64));
     CU_TRY(cudaMemcpy(h->d_ref, cfg->base_frame, h->N, cudaMemcpyHostToDevice)); // kernels.cu:406
@@ -520,6 +542,8 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
         cudaEvent_t *evs[] = {&s.ev_h2d0, &s.ev_h2d1, &s.ev_k0, &s.ev_k1, &s.ev_pos, &s.ev_p0, &s.ev_done};
         for (cudaEvent_t *e : evs) CU_TRY(cudaEventCreate(e));
     }
+    CU_TRY(cudaEventCreate(&h->ev_base));
+    CU_TRY(cudaEventRecord(h->ev_base, h->s_h2d));
     CU_TRY(cudaDeviceSynchronize());
     *out = h;
     return CVS_OK;
@@ -543,6 +567,7 @@ cvs_status cvs_destroy(cvs_handle h)
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    if (h->s_pay) cudaStreamDestroy(h->s_pay);
     delete h;
     return CVS_OK;
 }
@@ -579,9 +604,10 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     cvs_status st = check_handle(h);
     if (st) return st;
     if (!frame || !diff_out || !pos || !xs || !ticket) return fail(CVS_ERR_INVALID, "null argument");
-    Slot &s = h->slot[h->next_ticket & 1];
-    if (s.busy) return fail(CVS_ERR_INVALID, "two tickets are already outstanding; cvs_wait the oldest first");
+    Slot &s = h->slot[h->next_ticket % kSlots];
+    if (s.busy) return fail(CVS_ERR_INVALID, "%d tickets are already outstanding; cvs_wait the oldest first", kSlots);
 
+    const double th0 = h->trace ? host_us() : 0;
     // H2D (kernels.cu:461)
     CU_TRY(cudaEventRecord(s.ev_h2d0, h->s_h2d));
     CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
@@ -591,8 +617,10 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     CU_TRY(cudaEventRecord(s.ev_k0, h->s_comp));
     const size_t cap = round_up(h->N, 4);
     uint8_t *dshow = (h->mode && show) ? s.d_show : nullptr;
+    const double th1 = h->trace ? host_us() : 0;
     st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp);
     if (st) return st;
+    const double th2 = h->trace ? host_us() : 0;
     CU_TRY(cudaEventRecord(s.ev_k1, h->s_comp));
     // D2H of the count (kernels.cu:507) and of the display frame.  When the caller's payload buffers are
     // pinned (cvs_alloc_host) a copy kernel that reads the count on the device pushes exactly pos entries
@@ -600,7 +628,7 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     CU_TRY(cudaStreamWaitEvent(h->s_d2h, s.ev_k1, 0));
     CU_TRY(cudaEventRecord(s.ev_p0, h->s_d2h));
     void *dev_diff = nullptr, *dev_xs = nullptr;
-    s.pushed = mapped_device_pointer(diff_out, &dev_diff) && mapped_device_pointer(xs, &dev_xs) &&
+    s.pushed = h->push_payload && mapped_device_pointer(diff_out, &dev_diff) && mapped_device_pointer(xs, &dev_xs) &&
                ((uintptr_t)dev_diff % 16 == 0) && ((uintptr_t)dev_xs % 16 == 0);
     if (s.pushed) {
         cvs::k_payload_push<<<h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, (int *)dev_xs, (uint8_t *)dev_diff, cap);
@@ -611,6 +639,8 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
     if (dshow) CU_TRY(cudaMemcpyAsync(show, dshow, h->N, cudaMemcpyDeviceToHost, h->s_d2h));
     CU_TRY(cudaEventRecord(s.ev_pos, h->s_d2h));
+    if (h->trace)
+        fprintf(stderr, "submit host us: h2d %.1f run_frames %.1f d2h %.1f\n", th1 - th0, th2 - th1, host_us() - th2);
     s.busy = true;
     s.ticket = h->next_ticket++;
     s.u_frame = diff_out;
@@ -630,7 +660,7 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
 {
     cvs_status st = check_handle(h);
     if (st) return st;
-    Slot &s = h->slot[ticket & 1];
+    Slot &s = h->slot[ticket % kSlots];
     if (!s.busy || s.ticket != ticket) return fail(CVS_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
     s.busy = false;
     CU_TRY(cudaEventSynchronize(s.ev_pos));
@@ -638,21 +668,24 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
     if (st == CVS_ERR_INTERNAL) return st;
     const unsigned int n = *s.h_pos;
     // payload (kernels.cu:522-523): diff bytes over the head of the frame buffer, then the indices
-    if (n && !s.pushed) {
-        CU_TRY(cudaMemcpyAsync(s.u_frame, s.d_diff, n, cudaMemcpyDeviceToHost, h->s_d2h));
-        CU_TRY(cudaMemcpyAsync(s.u_xs, s.d_xs, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
+    // (on their own stream: s_d2h already holds the work of the younger tickets, and anything queued behind
+    // it would make this call wait for them)
+    s.copied = n && !s.pushed;
+    if (s.copied) {
+        CU_TRY(cudaMemcpyAsync(s.u_frame, s.d_diff, n, cudaMemcpyDeviceToHost, h->s_pay));
+        CU_TRY(cudaMemcpyAsync(s.u_xs, s.d_xs, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, h->s_pay));
+        CU_TRY(cudaEventRecord(s.ev_done, h->s_pay));
+        CU_TRY(cudaEventSynchronize(s.ev_done));
     }
-    CU_TRY(cudaEventRecord(s.ev_done, h->s_d2h));
-    CU_TRY(cudaEventSynchronize(s.ev_done));
     *s.u_pos = n;
-    float a = 0, b = 0, c = 0, d = 0;
-    CU_TRY(cudaEventElapsedTime(&a, s.ev_h2d0, s.ev_h2d1));
-    CU_TRY(cudaEventElapsedTime(&b, s.ev_k0, s.ev_k1));
-    CU_TRY(cudaEventElapsedTime(&c, s.ev_p0, s.ev_pos));
-    CU_TRY(cudaEventElapsedTime(&d, s.ev_pos, s.ev_done));
-    h->t_h2d = a * 1000.f;
-    h->t_kernel = b * 1000.f;
-    h->t_d2h = (c + d) * 1000.f;
+    h->last_slot = (int)(ticket % kSlots);
+    if (h->trace) { // CVS_TRACE=1: device timeline of every ticket on stderr (debug aid)
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        cudaEvent_t ev[6] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.copied ? s.ev_done : s.ev_pos};
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], h->ev_base, ev[i]);
+        fprintf(stderr, "ticket %llu h2d %.1f-%.1f kern %.1f-%.1f pos %.1f done %.1f us\n", (unsigned long long)ticket,
+                t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+    }
     return CVS_OK;
 }
 
@@ -667,6 +700,17 @@ cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *tex
 cvs_status cvs_get_timing(cvs_handle h, float *h2d_us, float *kernel_us, float *d2h_us)
 {
     if (!h) return fail(CVS_ERR_INVALID, "null handle");
+    if (h->last_slot >= 0) { // the events of the last completed ticket are read on demand, not per frame
+        Slot &s = h->slot[h->last_slot];
+        float a = 0, b = 0, c = 0, d = 0;
+        CU_TRY(cudaEventElapsedTime(&a, s.ev_h2d0, s.ev_h2d1));
+        CU_TRY(cudaEventElapsedTime(&b, s.ev_k0, s.ev_k1));
+        CU_TRY(cudaEventElapsedTime(&c, s.ev_p0, s.ev_pos));
+        if (s.copied) CU_TRY(cudaEventElapsedTime(&d, s.ev_pos, s.ev_done));
+        h->t_h2d = a * 1000.f;
+        h->t_kernel = b * 1000.f;
+        h->t_d2h = (c + d) * 1000.f;
+    }
     if (h2d_us) *h2d_us = h->t_h2d;
     if (kernel_us) *kernel_us = h->t_kernel;
     if (d2h_us) *d2h_us = h->t_d2h;

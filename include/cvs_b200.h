@@ -105,7 +105,7 @@ cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *tex
 
 /* Pipelined form of the same call: cvs_submit enqueues H2D + kernels + D2H on the stream's
  * double-buffered slots and returns a ticket; cvs_wait blocks until that frame's outputs are on
- * the host.  At most 2 tickets may be outstanding.  Host buffers must be pinned (cvs_alloc_host)
+ * the host.  At most 4 tickets may be outstanding; they complete in submission order.  Host buffers must be pinned (cvs_alloc_host)
  * for the copies to overlap. */
 cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text,
                       unsigned int *pos, int *xs, uint64_t *ticket);
