@@ -265,7 +265,8 @@ def ours(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (mean of the three densities) x frames per launch
+            traffic = json.load(fh)["dram_bytes_per_frame_mean"] * T
     except Exception:
         pass
 
