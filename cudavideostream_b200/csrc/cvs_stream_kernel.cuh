@@ -167,24 +167,33 @@ __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_
 __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
                                           int *xs_out, uint8_t *df_out, uint32_t g_lane, size_t cap, uint32_t lane)
 {
+    constexpr int kBatch = 4; // chunks in flight: their shuffles and shared loads are issued before any store
     const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll 8
-    for (uint32_t S = 0; S < 32; S++) { // unrolled: the shuffles of several chunks overlap
-        const uint32_t s0 = __shfl_sync(0xffffffffu, m[0], S), s1 = __shfl_sync(0xffffffffu, m[1], S),
-                       s2 = __shfl_sync(0xffffffffu, m[2], S);
-        uint32_t r = __shfl_sync(0xffffffffu, g_lane, S); // global rank of the chunk's first entry
-        const uint32_t cb = coff0 + S * kChunkBytes + lane, da = dvaddr0 + S * kChunkBytes + lane;
-        const uint32_t sm[3] = {s0, s1, s2};
+    for (uint32_t S0 = 0; S0 < 32; S0 += kBatch) {
+        uint32_t sm[kBatch][kMaskWords], r[kBatch], v[kBatch][kMaskWords];
 #pragma unroll
-        for (int w = 0; w < kMaskWords; w++) {
-            if ((sm[w] >> lane) & 1u) {
-                const uint32_t g = r + (uint32_t)__popc(sm[w] & lt);
-                if (g < cap) {
+        for (int i = 0; i < kBatch; i++) {
+#pragma unroll
+            for (int w = 0; w < kMaskWords; w++) sm[i][w] = __shfl_sync(0xffffffffu, m[w], S0 + i);
+            r[i] = __shfl_sync(0xffffffffu, g_lane, S0 + i); // global rank of the chunk's first entry
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; i++)
+#pragma unroll
+            for (int w = 0; w < kMaskWords; w++) v[i][w] = lds_u8(dvaddr0 + (S0 + i) * kChunkBytes + lane + 32 * w);
+#pragma unroll
+        for (int i = 0; i < kBatch; i++) {
+            const uint32_t cb = coff0 + (S0 + i) * kChunkBytes + lane;
+            uint32_t rr = r[i];
+#pragma unroll
+            for (int w = 0; w < kMaskWords; w++) {
+                const uint32_t g = rr + (uint32_t)__popc(sm[i][w] & lt);
+                if (((sm[i][w] >> lane) & 1u) && g < cap) {
                     stg_stream_u32(xs_out + g, cb + 32 * w);
-                    stg_stream_u8(df_out + g, lds_u8(da + 32 * w));
+                    stg_stream_u8(df_out + g, v[i][w]);
                 }
+                rr += (uint32_t)__popc(sm[i][w]);
             }
-            r += (uint32_t)__popc(sm[w]);
         }
     }
 }
