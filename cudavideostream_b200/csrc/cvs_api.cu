@@ -267,7 +267,16 @@ cvs_status launch_conv(const uint8_t *in, uint8_t *out, int width, int height, s
     const int rowbytes = 3 * width;
     const bool fast = (rowbytes % 4 == 0) && (in_stride % 4 == 0) && (out_stride % 4 == 0) &&
                       ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0) && (K == 1 || K == 3 || K == 5);
-    if (fast) {
+    if (fast && K == 3) {
+        // non-negative weights with a modest sum keep every accumulator inside [0, 2^23): cheap truncation
+        bool nonneg = true;
+        float sum = 0.f;
+        for (int i = 0; i < 9; i++) { nonneg = nonneg && w.k[i] >= 0.f; sum += w.k[i]; }
+        nonneg = nonneg && sum <= 16384.f;
+        dim3 block(128), grid((rowbytes / 4 + 127) / 128, (height + cvs::kConvRows - 1) / cvs::kConvRows, nframes);
+        if (nonneg) cvs::k_conv3_strip<true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        else cvs::k_conv3_strip<false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+    } else if (fast) {
         dim3 block(256), grid((rowbytes / 4 + 255) / 256, height, nframes);
         switch (K) {
         case 1: cvs::k_conv_rows4<1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;

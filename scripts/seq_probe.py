@@ -12,6 +12,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--mode", type=int, default=0)
+ap.add_argument("--noise", type=int, default=0, help="K of the gaussian noise filter (0 = off)")
 a = ap.parse_args()
 W, H, T = a.width, a.height, a.frames
 N = 3 * W * H
@@ -23,7 +24,15 @@ for t in range(T):
     cvs.synth.next_frame_device(fr.data_ptr() + t * S, fr.data_ptr() + (t + 1) * S, W, H, 1, t, a.density, st)
 torch.cuda.synchronize()
 cap = (N + 3) // 4 * 4
-s = cvs.Stream(W, H, fr[:N].cpu().numpy(), mode=a.mode, max_sequence=max(T, 16))
+kw = {}
+if a.noise:
+    K = a.noise
+    sig = K * K / 6.0
+    x = np.arange(K, dtype=np.float32) - (K - 1) / 2.0
+    g = (1.0 / (2.0 * np.pi * sig * sig)) * np.exp(-((x[:, None] ** 2 + x[None, :] ** 2) / (2.0 * sig * sig)))
+    g = g.astype(np.float32); g /= g.sum(dtype=np.float32)
+    kw = dict(noise_filter=True, ksize=K, kweights=g)
+s = cvs.Stream(W, H, fr[:N].cpu().numpy(), mode=a.mode, max_sequence=max(T, 16), **kw)
 pos = torch.zeros(T, dtype=torch.int32, device="cuda")
 xs = torch.empty(T * cap, dtype=torch.int32, device="cuda")
 df = torch.empty(T * cap, dtype=torch.uint8, device="cuda")
@@ -43,5 +52,5 @@ except Exception as e:
     print("status:", e)
 sp = int(pos.to(torch.int64).sum())
 m = min(ms)
-print(f"flags={os.environ.get('CVS_DEBUG_FLAGS','0')} {W}x{H} T={T} d={a.density} mode={a.mode} c={sp/(T*N):.4f} "
+print(f"flags={os.environ.get('CVS_DEBUG_FLAGS','0')} {W}x{H} T={T} d={a.density} mode={a.mode} noiseK={a.noise} c={sp/(T*N):.4f} "
       f"best {m:.3f} ms  {m*1000/T:.2f} us/frame  hbm_model {(T*(N+4)+5*sp)/m/1e6:.0f} GB/s  alg {(T*(2*N+4)+6*sp)/m/1e6:.0f} GB/s")
