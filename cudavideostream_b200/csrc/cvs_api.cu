@@ -348,8 +348,8 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     }
 
     // ---- geometry of the persistent launch
-    int G = 2 * h->sms;
-    if (G > 2 * cvs::kThreads) G = 2 * cvs::kThreads; // the look-back reads two predecessors per thread
+    int G = cvs::kBlocksPerSM * h->sms;
+    if (G > cvs::kLook * cvs::kThreads) G = cvs::kLook * cvs::kThreads; // the look-back reads kLook predecessors per thread
     if ((uint32_t)G > h->nchunks) G = (int)h->nchunks;
     uint32_t nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));

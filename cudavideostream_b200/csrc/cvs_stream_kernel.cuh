@@ -50,8 +50,13 @@
 
 namespace cvs {
 
-constexpr int kThreads = 256;                         // threads per block
+#ifndef CVS_STREAM_THREADS
+#define CVS_STREAM_THREADS 256
+#endif
+constexpr int kThreads = CVS_STREAM_THREADS;           // threads per block
 constexpr int kWarps = kThreads / 32;
+constexpr int kBlocksPerSM = 512 / kThreads;          // 128 registers per thread fill the register file
+constexpr int kLook = (148 * kBlocksPerSM + kThreads - 1) / kThreads + 1; // look-back descriptors a thread may read
 constexpr int kGroupsPerThread = 2;
 constexpr int kChunkBytes = kGroupsPerThread * kGroupBytes;   // 96
 constexpr int kChunkWords = kChunkBytes / 4;                  // 24
@@ -200,22 +205,25 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
 
 __device__ __forceinline__ uint32_t warp_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// sum of the first n (<= 8) and of all 8 words at p (two broadcast 16-byte shared loads, no shuffles)
-__device__ __forceinline__ void sum8(const uint32_t *p, uint32_t n, uint32_t &first_n, uint32_t &all)
+// sum of the first n and of all kWarps words at p (broadcast 16-byte shared loads, no shuffles)
+__device__ __forceinline__ void sum_warps(const uint32_t *p, uint32_t n, uint32_t &first_n, uint32_t &all)
 {
-    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + 4);
-    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    static_assert(kWarps % 4 == 0, "warp totals are read as 16-byte vectors");
     first_n = 0; all = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        if ((uint32_t)i < n) first_n += v[i];
-        all += v[i];
+    for (int q4 = 0; q4 < kWarps / 4; q4++) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(p + 4 * q4);
+        const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if ((uint32_t)(4 * q4 + i) < n) first_n += v[i];
+            all += v[i];
+        }
     }
 }
-static_assert(kWarps == 8, "sum8 assumes eight warps per block");
 
 template <int MODE, bool HI, bool REFREG>
-__global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t *slut = reinterpret_cast<uint32_t *>(smem + SmemLayout::lut);
@@ -327,13 +335,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
         // ---- back half, part 1: start fetching the look-back descriptors of step q-1.  Thread i reads
         //      predecessors i, i+256, ...; thread b%256 also reads the running total of the earlier segments
-        unsigned long long pv0 = 0, pv1 = 0, pv2 = 0;
+        unsigned long long pv[kLook], pv2 = 0;
         const unsigned long long *prow = p.desc + (size_t)(q ? q - 1 : 0) * (G + 1);
         const bool look = pending && !(p.debug & 1u);
-        const bool has0 = look && tid < b, has1 = look && tid + kThreads < b;
-        const bool has2 = look && b_s > 0 && tid == (b & (kThreads - 1));
-        if (has0) pv0 = desc_peek(prow + tid);
-        if (has1) pv1 = desc_peek(prow + tid + kThreads);
+        const bool has2 = look && b_s > 0 && tid == (b % kThreads);
+#pragma unroll
+        for (int i = 0; i < kLook; i++) {
+            pv[i] = 0;
+            if (look && tid + i * kThreads < b) pv[i] = desc_peek(prow + tid + i * kThreads);
+        }
         if (has2) pv2 = desc_peek(prow - 1); // slot G of the previous step
 
         uint32_t m[kMaskWords] = {0, 0, 0};
@@ -478,10 +488,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
                 return (uint32_t)v;
             };
             uint32_t part = 0;
-            if (has0) part += settle(pv0, prow + tid);
-            if (has1) part += settle(pv1, prow + tid + kThreads);
+#pragma unroll
+            for (int i = 0; i < kLook; i++)
+                if (look && tid + i * kThreads < b) part += settle(pv[i], prow + tid + i * kThreads);
             if (has2) part += settle(pv2, prow - 1);
-            // G <= 2 * kThreads is enforced by the host, so two reads per thread cover every predecessor
+            // G <= kLook * kThreads is enforced by the host, so kLook reads per thread cover every predecessor
             part = warp_add(part);
             if (lane == 0) red[(q & 1u) * kWarps + warp] = part;
         }
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
         uint32_t total = 0, wexc = 0, wtotal = 0;
         if (front) {
-            sum8(wtot + (q & 1u) * kWarps, warp, wexc, total); // entries of the warps before this one / of the block
+            sum_warps(wtot + (q & 1u) * kWarps, warp, wexc, total); // entries of the warps before this one / of the block
             if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
             incl = warp_incl_scan(cnt, lane);
             wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
@@ -498,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_stream(const StreamParams p)
 
         if (pending) {
             uint32_t base, unused;
-            sum8(red + (q & 1u) * kWarps, 0, unused, base);
+            sum_warps(red + (q & 1u) * kWarps, 0, unused, base);
             if (tid == 0) {
                 if (b == G - 1) {
                     desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
