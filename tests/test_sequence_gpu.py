@@ -192,3 +192,46 @@ def test_standalone_filters(cvs, oracle):
     ht = d_ht.cpu().numpy()
     assert np.array_equal(ht[:256], hist) and ht[256] == thr
     assert np.array_equal(d_o[:n].cpu().numpy(), oracle.binarize(np.repeat(g1, 3), thr))
+
+
+@pytest.mark.parametrize("w,h,mode", [(1919, 1079, 0), (641, 359, 1), (250, 130, 5), (7, 5, 3)])
+def test_no_write_outside_the_buffers(cvs, w, h, mode):
+    # compute-sanitizer is closed on the pool, so out-of-bounds writes are caught with guard bands: every output
+    # buffer of the sequence API sits inside a larger allocation filled with a pattern that must survive.  (The
+    # reference's kernel2 over-writes 5,120 bytes past its buffers, SURVEY section 2a -- this one must not.)
+    import torch
+    G = 4096
+    nframes, n = 3, 3 * w * h
+    stride = (n + 15) // 16 * 16
+    cap = (n + 3) // 4 * 4
+    base, frames = random_sequence(w, h, nframes, 1.0, seed=5)   # every byte changes: payload fills the capacity
+
+    def guarded(nbytes, dtype=torch.uint8):
+        raw = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + nbytes].view(dtype)
+
+    raw_f, d_frames = guarded(nframes * stride)
+    for t in range(nframes):
+        d_frames[t * stride: t * stride + n] = torch.from_numpy(frames[t]).cuda()
+    raw_p, d_pos = guarded(4 * nframes, torch.int32)
+    raw_x, d_xs = guarded(4 * nframes * cap, torch.int32)
+    raw_d, d_diff = guarded(nframes * cap)
+    raw_s, d_show = guarded(nframes * stride)
+    s = cvs.Stream(w, h, base, mode=mode)
+    s.run_sequence_device(d_frames.data_ptr(), stride, nframes, d_pos.data_ptr(), d_xs.data_ptr(), d_diff.data_ptr(),
+                          cap, d_show.data_ptr() if mode else 0, stride,
+                          cuda_stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    s.sequence_status()
+    assert d_pos.cpu().tolist() == [n] * nframes
+    for raw in (raw_f, raw_p, raw_x, raw_d, raw_s):
+        assert bool((raw[:G] == 0xA5).all()) and bool((raw[-G:] == 0xA5).all())
+    if not mode:
+        assert bool((d_show == 0xA5).all())          # no display buffer requested: untouched
+    else:
+        for t in range(nframes):                      # the pad between frames of the display buffer is untouched too
+            assert bool((d_show[t * stride + n:(t + 1) * stride] == 0xA5).all())
+    # the input frames are never modified
+    for t in range(nframes):
+        assert np.array_equal(d_frames[t * stride: t * stride + n].cpu().numpy(), frames[t])
+    s.close()
