@@ -412,7 +412,7 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     }
 
     if (binarize) {
-        cvs::k_threshold<<<(nframes + 63) / 64, 64, 0, st>>>(h->d_hist, h->d_thr, nframes, 50, 200);
+        cvs::k_threshold<<<nframes, 256, 0, st>>>(h->d_hist, h->d_thr, nframes, 50, 200);
         CU_TRY(cudaGetLastError());
         dim3 grid(grid_for((h->npix + 15) / 16, 256, h->sms), nframes);
         cvs::k_binarize_expand<<<grid, 256, 0, st>>>(h->d_gray1, h->P16, d_show, show_stride, h->d_thr, h->npix);
@@ -872,7 +872,7 @@ cvs_status cvs_binarize_device(const uint8_t *d_frame, uint8_t *d_out, uint8_t *
     CU_TRY(cudaMemsetAsync(d_hist_thr, 0, 257 * sizeof(int), s));
     st = gray_launch(d_frame, d_gray, 3u * npix, weighted, 1, (unsigned int *)d_hist_thr, sms, s);
     if (st) return st;
-    cvs::k_threshold<<<1, 32, 0, s>>>((const unsigned int *)d_hist_thr, d_hist_thr + 256, 1, clamp_lo, clamp_hi);
+    cvs::k_threshold<<<1, 256, 0, s>>>((const unsigned int *)d_hist_thr, d_hist_thr + 256, 1, clamp_lo, clamp_hi);
     CU_TRY(cudaGetLastError());
     cvs::k_binarize_expand<<<dim3(grid_for((npix + 15) / 16, 256, sms), 1), 256, 0, s>>>(d_gray, 0, d_out, 0,
                                                                                         d_hist_thr + 256, npix);

@@ -193,29 +193,51 @@ __global__ void __launch_bounds__(256) k_overlay(uint8_t *frames, size_t stride,
 }
 
 // ------------------------------------------------------------------------------------------------
-// A7 "two max" threshold: the CPU loop restated literally (server/src/server.cpp:108-127), one
-// thread per frame.  ht: [nframes][256] histogram; thr: [nframes].
+// A7 "two max" threshold (server/src/server.cpp:108-127).  The CPU loop keeps a running arg-max with ">=":
+// index_max ends as the LAST bin that holds the global maximum and -- because sec_max is overwritten with the new
+// maximum, so the else-branch can never fire -- index_sec_max ends as the running arg-max just before that, i.e.
+// the previous "record" bin (a bin whose count is >= every count before it), or -1.  One 256-thread block per
+// frame finds the records with a prefix maximum and picks the last two.   hist: [nframes][256]; thr: [nframes].
 // ------------------------------------------------------------------------------------------------
-__global__ void k_threshold(const unsigned int *__restrict__ hist, int *__restrict__ thr, int nframes, int clamp_lo,
-                            int clamp_hi)
+__global__ void __launch_bounds__(256) k_threshold(const unsigned int *__restrict__ hist, int *__restrict__ thr,
+                                                   int nframes, int clamp_lo, int clamp_hi)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned int wmax[8];
+    __shared__ unsigned int rec[8];
+    const int t = blockIdx.x, i = threadIdx.x, lane = i & 31, warp = i >> 5;
     if (t >= nframes) return;
-    const unsigned int *h = hist + (size_t)t * 256;
-    long long mx = -1;
-    int imax = -1, isec = -1;
-    for (int i = 0; i < 256; i++) {
-        const long long v = (long long)h[i];
-        if (v >= mx) { // the else-branch of the reference can never fire: sec_max is set to the new max
-            isec = imax;
-            imax = i;
-            mx = v;
-        }
+    const unsigned int v = hist[(size_t)t * 256 + i];
+    unsigned int inc = v; // inclusive prefix maximum inside the warp
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc = max(inc, n);
     }
-    int th = (imax + isec) / 2;
-    if (th < clamp_lo) th = clamp_lo;
-    if (th > clamp_hi) th = clamp_hi;
-    thr[t] = th;
+    if (lane == 31) wmax[warp] = inc;
+    __syncthreads();
+    unsigned int before = 0; // maximum of every earlier bin (0 when there is none: counts are >= 0)
+    for (int w = 0; w < warp; w++) before = max(before, wmax[w]);
+    const unsigned int prev = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane > 0) before = max(before, prev);
+    const unsigned int b = __ballot_sync(0xffffffffu, v >= before); // bin 0 is always a record (max starts at -1)
+    if (lane == 0) rec[warp] = b;
+    __syncthreads();
+    if (i == 0) {
+        int imax = -1, isec = -1;
+        for (int w = 7; w >= 0 && isec < 0; w--) {
+            unsigned int m = rec[w];
+            while (m && isec < 0) {
+                const int bit = 31 - __clz((int)m);
+                m &= ~(1u << bit);
+                if (imax < 0) imax = 32 * w + bit;
+                else isec = 32 * w + bit;
+            }
+        }
+        int th = (imax + isec) / 2; // C division: (0 + -1) / 2 == 0
+        if (th < clamp_lo) th = clamp_lo;
+        if (th > clamp_hi) th = clamp_hi;
+        thr[t] = th;
+    }
 }
 
 // A6 binarize pass 2: gray1 (1 B/pixel) -> 3-channel 0/255 image   (server.cpp:129-135)

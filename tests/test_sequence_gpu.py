@@ -235,3 +235,34 @@ def test_no_write_outside_the_buffers(cvs, w, h, mode):
     for t in range(nframes):
         assert np.array_equal(d_frames[t * stride: t * stride + n].cpu().numpy(), frames[t])
     s.close()
+
+
+@pytest.mark.parametrize("levels", [[0], [1], [100], [255], [10, 200], [200, 10], [50, 50, 90], [0, 255, 255]])
+def test_threshold_quirks_on_gpu(cvs, oracle, levels):
+    # histograms that hit the corners of the two-max loop (server.cpp:108-127): arg-max at bin 0 (isec = -1), ties,
+    # records before the maximum, both clamps -- through the real pipeline (average gray, clamp [50,200] and [0,255])
+    import torch
+    w, h = 64, 48
+    p = w * h
+    px = np.zeros((p, 3), dtype=np.uint8)
+    bounds = np.linspace(0, p, len(levels) + 1).astype(int)
+    if len(levels) == 3:
+        bounds = np.array([0, p // 4, p // 2, p])  # unequal counts
+    for i, g in enumerate(levels):
+        px[bounds[i]:bounds[i + 1]] = g
+    frame = px.reshape(-1)
+    d_in = torch.from_numpy(np.concatenate([frame, np.zeros(64, np.uint8)])).cuda()
+    d_out = torch.zeros(3 * p + 64, dtype=torch.uint8, device="cuda")
+    d_g = torch.zeros(p + 64, dtype=torch.uint8, device="cuda")
+    d_ht = torch.zeros(257, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    g1 = oracle.gray_avg1(frame, w, h)
+    hist = oracle.histogram1(g1)
+    for lo, hi in ((50, 200), (0, 255), (20, 255)):
+        cvs.filters.binarize(d_in.data_ptr(), d_out.data_ptr(), d_g.data_ptr(), d_ht.data_ptr(), w, h, False, lo, hi, st)
+        torch.cuda.synchronize()
+        thr = oracle.threshold_twomax(hist, lo, hi)
+        ht = d_ht.cpu().numpy()
+        assert np.array_equal(ht[:256], hist)
+        assert ht[256] == thr, f"levels {levels} clamp [{lo},{hi}]: {ht[256]} != {thr}"
+        assert np.array_equal(d_out[:3 * p].cpu().numpy(), oracle.binarize(np.repeat(g1, 3), thr))
