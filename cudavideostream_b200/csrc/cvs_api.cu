@@ -267,22 +267,24 @@ cvs_status launch_conv(const uint8_t *in, uint8_t *out, int width, int height, s
     const int rowbytes = 3 * width;
     const bool fast = (rowbytes % 4 == 0) && (in_stride % 4 == 0) && (out_stride % 4 == 0) &&
                       ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0) && (K == 1 || K == 3 || K == 5);
-    if (fast && K == 3) {
+    // K = 1 keeps the one-row kernel; K >= 7 falls to the byte kernel (a K-row float window no longer fits in registers)
+    if (fast && (K == 3 || K == 5)) {
         // non-negative weights with a modest sum keep every accumulator inside [0, 2^23): cheap truncation
         bool nonneg = true;
         float sum = 0.f;
-        for (int i = 0; i < 9; i++) { nonneg = nonneg && w.k[i] >= 0.f; sum += w.k[i]; }
+        for (int i = 0; i < K * K; i++) { nonneg = nonneg && w.k[i] >= 0.f; sum += w.k[i]; }
         nonneg = nonneg && sum <= 16384.f;
         dim3 block(128), grid((rowbytes / 4 + 127) / 128, (height + cvs::kConvRows - 1) / cvs::kConvRows, nframes);
-        if (nonneg) cvs::k_conv3_strip<true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
-        else cvs::k_conv3_strip<false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        if (K == 3) {
+            if (nonneg) cvs::k_conv_strip<3, true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            else cvs::k_conv_strip<3, false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        } else {
+            if (nonneg) cvs::k_conv_strip<5, true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            else cvs::k_conv_strip<5, false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        }
     } else if (fast) {
         dim3 block(256), grid((rowbytes / 4 + 255) / 256, height, nframes);
-        switch (K) {
-        case 1: cvs::k_conv_rows4<1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
-        case 3: cvs::k_conv_rows4<3><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
-        default: cvs::k_conv_rows4<5><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w); break;
-        }
+        cvs::k_conv_rows4<1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
     } else {
         dim3 block(256), grid((rowbytes + 255) / 256, height, nframes);
         cvs::k_conv_bytes<<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, K, w);

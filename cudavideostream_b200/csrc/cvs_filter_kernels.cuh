@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(256) k_conv_rows4(const uint8_t *__restrict__ 
     reinterpret_cast<uint32_t *>(fout + (size_t)row * rowbytes)[xw] = pk;
 }
 
-// K = 3 (the reference's configuration, common.h:6), register-blocked: a thread produces a strip of 4 bytes x
-// kConvRows rows.  Each input row is fetched once per strip (three aligned words through L1), each of its ten
-// bytes becomes a float once (PRMT into the mantissa of 2^23, one FADD) and stays in a three-row register window,
-// so an output costs 9 FFMA -- in the same row-major tap order as k_conv_rows4, hence the same bits.
+// K = 3 (the reference's configuration, common.h:6) and K = 5, register-blocked: a thread produces a strip of
+// 4 bytes x kConvRows rows.  Each input row is fetched once per strip (aligned words through L1), each of its
+// 4 + 6*(K/2) bytes becomes a float once (PRMT into the mantissa of 2^23, one FADD) and stays in a K-row register
+// window, so an output costs K*K FFMA -- in the same row-major tap order as k_conv_rows4, hence the same bits.
 // NONNEG: all weights >= 0, so 0 <= acc < 2^23 and truncation is one FADD.RZ against 2^23 instead of F2I.
 constexpr int kConvRows = 8;
 
@@ -88,11 +88,12 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) // b: compi
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)b)) - 8388608.0f;
 }
 
-template <bool NONNEG>
-__global__ void __launch_bounds__(128) k_conv3_strip(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int width,
-                                                     int height, size_t in_stride, size_t out_stride,
-                                                     const __grid_constant__ ConvWeights w)
+template <int K, bool NONNEG>
+__global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int width,
+                                                    int height, size_t in_stride, size_t out_stride,
+                                                    const __grid_constant__ ConvWeights w)
 {
+    constexpr int R = K / 2, HALO = 3 * R, WL = (HALO + 3) / 4, NW = 1 + 2 * WL, NF = 4 + 2 * HALO;
     const int rowbytes = 3 * width;
     const int wordsperrow = rowbytes >> 2;
     const int xw = blockIdx.x * blockDim.x + threadIdx.x; // word column
@@ -100,36 +101,38 @@ __global__ void __launch_bounds__(128) k_conv3_strip(const uint8_t *__restrict__
     if (xw >= wordsperrow) return;
     const uint8_t *fin = in + (size_t)blockIdx.z * in_stride;
     uint8_t *fout = out + (size_t)blockIdx.z * out_stride;
-    const bool has_l = xw > 0, has_r = xw + 1 < wordsperrow;
 
-    float f[3][10]; // window: bytes x-3 .. x+6 of three consecutive input rows
-    auto load_row = [&](int rr, float (&dst)[10]) {
-        uint32_t a = 0, b = 0, c = 0;
-        if (rr >= 0 && rr < height) {
-            const uint32_t *rp = reinterpret_cast<const uint32_t *>(fin + (size_t)rr * rowbytes) + xw;
-            b = __ldg(rp);
-            if (has_l) a = __ldg(rp - 1);
-            if (has_r) c = __ldg(rp + 1);
+    float f[K][NF]; // window: bytes x-HALO .. x+3+HALO of K consecutive input rows
+    auto load_row = [&](int rr, float (&dst)[NF]) {
+        uint32_t wd[NW];
+#pragma unroll
+        for (int u = 0; u < NW; u++) {
+            const int xi = xw + u - WL;
+            wd[u] = 0u;
+            if (rr >= 0 && rr < height && xi >= 0 && xi < wordsperrow)
+                wd[u] = __ldg(reinterpret_cast<const uint32_t *>(fin + (size_t)rr * rowbytes) + xi);
         }
-        dst[0] = byte_to_float(a, 1); dst[1] = byte_to_float(a, 2); dst[2] = byte_to_float(a, 3);
-        dst[3] = byte_to_float(b, 0); dst[4] = byte_to_float(b, 1); dst[5] = byte_to_float(b, 2); dst[6] = byte_to_float(b, 3);
-        dst[7] = byte_to_float(c, 0); dst[8] = byte_to_float(c, 1); dst[9] = byte_to_float(c, 2);
+#pragma unroll
+        for (int n = 0; n < NF; n++) {
+            const int bi = 4 * WL - HALO + n; // byte index inside wd[]
+            dst[n] = byte_to_float(wd[bi >> 2], bi & 3);
+        }
     };
-    load_row(row0 - 1, f[0]);
-    load_row(row0, f[1]);
+#pragma unroll
+    for (int i = 0; i < K - 1; i++) load_row(row0 - R + i, f[i]);
 #pragma unroll
     for (int r = 0; r < kConvRows; r++) {
         const int row = row0 + r;
         if (row >= height) break;
-        load_row(row + 1, f[(r + 2) % 3]);
+        load_row(row + R, f[(r + K - 1) % K]);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < K; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                const float kw = w.k[i * 3 + j];
+            for (int j = 0; j < K; j++) {
+                const float kw = w.k[i * K + j];
 #pragma unroll
-                for (int o = 0; o < 4; o++) acc[o] = __fmaf_rn(kw, f[(r + i) % 3][o + 3 * j], acc[o]);
+                for (int o = 0; o < 4; o++) acc[o] = __fmaf_rn(kw, f[(r + i) % K][o + 3 * j], acc[o]);
             }
         uint32_t pk;
         if (NONNEG) {
