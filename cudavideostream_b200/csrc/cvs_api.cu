@@ -357,10 +357,12 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
     StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
+    // ring depth: see nstages in k_stream
+    const int smem_bytes = cvs::SmemLayout::total(refreg ? cvs::kStages : cvs::kStages - 1);
     int &occ = h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
     if (occ == 0) { // first launch of this variant on this handle
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cvs::SmemLayout::total));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, cvs::SmemLayout::total));
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, smem_bytes));
     }
     if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
     if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
@@ -408,7 +410,7 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.status = h->d_status;
         void *args[] = {&p};
         CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(cvs::kThreads), args,
-                                           (size_t)cvs::SmemLayout::total, st));
+                                           (size_t)smem_bytes, st));
         h->launches++;
         done += chunk;
     }
