@@ -167,6 +167,15 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # one host thread + one context per GPU, pinned buffers NUMA-local to it: bind this rank
+        # to the CPUs nearest its GPU before any pinned allocation is first touched
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
+    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cvs.load_library()
     st = torch.cuda.current_stream().cuda_stream
