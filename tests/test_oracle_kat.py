@@ -118,3 +118,48 @@ def test_golden_k1_record():
     with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
         g = json.load(f)
     assert g["changed_bytes"] == 369350 and g["total_bytes"] == 6220800
+
+
+def test_a1_matches_an_independent_numpy_restatement(oracle):
+    # second, independent statement of tests/cuda_streaming/test.cu:560-576 (vectorised numpy) on random frames,
+    # including the wrap cases of the uint8 difference and several thresholds
+    rng = np.random.default_rng(7)
+    for n, thr in ((1, 20), (97, 20), (4096, 0), (4096, 20), (4099, 127), (5000, 200), (333, 255), (333, -1)):
+        prev = rng.integers(0, 256, size=n, dtype=np.uint8)
+        cur = rng.integers(0, 256, size=n, dtype=np.uint8)
+        near = rng.random(n) < 0.5  # half the bytes close to the reference so both branches are exercised
+        cur = np.where(near, np.clip(prev.astype(int) + rng.integers(-25, 26, size=n), 0, 255), cur).astype(np.uint8)
+        df = cur.astype(np.int32) - prev.astype(np.int32)
+        changed = (df < -thr) | (df > thr)
+        pos, xs, diff, ref, after = oracle.diff_compact(cur, prev, thr)
+        assert pos == int(changed.sum())
+        assert np.array_equal(xs, np.flatnonzero(changed).astype(np.int32))
+        assert np.array_equal(diff, (df[changed] & 0xFF).astype(np.uint8))
+        assert np.array_equal(ref, np.where(changed, cur, prev))
+        # the payload overwrites the head of the frame buffer, the tail keeps the input (kernels.cu:522)
+        assert np.array_equal(after[pos:], cur[pos:]) and np.array_equal(after[:pos], diff)
+        assert np.array_equal(oracle.client_apply(prev, xs, diff), ref)
+
+
+def test_filters_match_independent_numpy_restatements(oracle):
+    rng = np.random.default_rng(11)
+    w, h = 37, 23
+    a = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    b = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    # gray average / weighted (server.cpp:96-101, grayscale-weighted/cpu.cu:38-42)
+    assert np.array_equal(oracle.gray_avg1(a, w, h), (a.astype(int).sum(axis=2) // 3).astype(np.uint8).reshape(-1))
+    wg = (0.114 * a[:, :, 0].astype(np.float64) + 0.587 * a[:, :, 1].astype(np.float64)) + 0.299 * a[:, :, 2].astype(np.float64)
+    assert np.array_equal(oracle.gray_weighted1(a, w, h), wg.astype(np.uint8).reshape(-1))
+    # red map (heat_map_red_benchmark/cpu.cu:38-55)
+    ch = (np.abs(a.astype(int) - b.astype(int)) > 20).any(axis=2)
+    red = np.zeros((h, w, 3), dtype=np.uint8)
+    red[:, :, 2] = np.where(ch, 255, 0)
+    assert np.array_equal(oracle.red_map(a, b, w, h, 20), red.reshape(-1))
+    # heat map (heat_map_benchmark/cpu.cu:19-27,54-66)
+    d = np.abs(a.astype(int) - b.astype(int)).sum(axis=2)
+    x = (d / 510.0).astype(np.float32).astype(np.float64)
+    r = np.minimum(np.maximum(np.sin(np.pi * x - np.pi / 2.0) * 255.0, 0.0), 255.0).astype(int)
+    g = np.minimum(np.maximum(np.sin(np.pi * x) * 255.0, 0.0), 255.0).astype(int)
+    bl = np.minimum(np.maximum(np.sin(np.pi * x + np.pi / 2.0) * 255.0, 0.0), 255.0).astype(int)
+    heat = np.stack([bl, g, r], axis=2).astype(np.uint8)
+    assert np.array_equal(oracle.heat_map(a, b, w, h), heat.reshape(-1))
