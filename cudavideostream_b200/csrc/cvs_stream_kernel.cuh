@@ -178,6 +178,9 @@ __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_
 __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
                                           int *xs_out, uint8_t *df_out, uint32_t g_lane, size_t cap, uint32_t lane)
 {
+    // 32-bit ranks and one-instruction bit tests: this loop is the bulk of a dense frame's instructions
+    const uint32_t cap32 = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap;
+    const uint32_t lanebit = 1u << lane;
     constexpr int kBatch = 4; // chunks in flight: their shuffles and shared loads are issued before any store
     const uint32_t lt = (1u << lane) - 1u;
     for (uint32_t S0 = 0; S0 < 32; S0 += kBatch) {
@@ -199,7 +202,7 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
 #pragma unroll
             for (int w = 0; w < kMaskWords; w++) {
                 const uint32_t g = rr + (uint32_t)__popc(sm[i][w] & lt);
-                if (((sm[i][w] >> lane) & 1u) && g < cap) {
+                if ((sm[i][w] & lanebit) && g < cap32) {
                     stg_stream_u32(xs_out + g, cb + 32 * w);
                     stg_stream_u8(df_out + g, v[i][w]);
                 }
