@@ -105,12 +105,22 @@ def host_ring(nring: int, density_ppm: int, seed: int):
     return base, ring
 
 
+_RINGS = None
+
+
+def cpu_rings():
+    """Host frame rings of the three densities (generated once per process: the numpy camera is slow)."""
+    global _RINGS
+    if _RINGS is None:
+        _RINGS = [host_ring(4, d, 0xC0DA5EED) for d in DENSITIES_PPM]
+    return _RINGS
+
+
 def cpu_run(target_seconds: float, threads: int):
     """Times the CPU path on a bounded sample.  Returns dict(value=frames/s, cores, sample, ...)."""
     from oracle import oracle as orc
     orc.build()
-    nring = 4
-    rings = [host_ring(nring, d, 0xC0DA5EED) for d in DENSITIES_PPM]
+    rings = cpu_rings()
     # calibrate: one frame per thread per density
     t_cal = sum(orc.bench_diff_compact(r, b, THR, 1, threads)[0] for b, r in rings)
     iters = max(1, int(target_seconds / max(t_cal, 1e-3)))
