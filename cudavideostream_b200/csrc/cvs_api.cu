@@ -444,6 +444,10 @@ cvs_status status_word(cvs_handle h)
 
 } // namespace
 
+namespace {
+cvs_status init_device_state(cvs_handle h, const cvs_config *cfg);
+}
+
 extern "C" {
 
 const char *cvs_last_error(void) { return g_err; }
@@ -516,6 +520,22 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
+    const cvs_status st = init_device_state(h, cfg);
+    if (st != CVS_OK) { // g_err already holds the reason; release whatever was allocated
+        cvs_destroy(h);
+        return st;
+    }
+    *out = h;
+    return CVS_OK;
+}
+
+} // extern "C"
+
+namespace {
+
+// device-side half of cvs_create: streams, events, the reference frame, per-slot buffers
+cvs_status init_device_state(cvs_handle h, const cvs_config *cfg)
+{
     CU_TRY(cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, cfg->device));
 
     CU_TRY(cudaStreamCreateWithFlags(&h->s_comp, cudaStreamNonBlocking));
@@ -558,9 +578,12 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     CU_TRY(cudaEventCreate(&h->ev_base));
     CU_TRY(cudaEventRecord(h->ev_base, h->s_h2d));
     CU_TRY(cudaDeviceSynchronize());
-    *out = h;
     return CVS_OK;
 }
+
+} // namespace
+
+extern "C" {
 
 cvs_status cvs_destroy(cvs_handle h)
 {
@@ -577,6 +600,7 @@ cvs_status cvs_destroy(cvs_handle h)
     cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
     cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
     cudaFree(h->d_glyphs);
+    if (h->ev_base) cudaEventDestroy(h->ev_base);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
