@@ -1,0 +1,52 @@
+"""The built library really contains the sm_100a features DESIGN.md claims (checked in the SASS, no GPU needed)."""
+import functools
+import re
+import shutil
+import subprocess
+
+import pytest
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@functools.lru_cache(maxsize=1)
+def _sass() -> str:
+    import cudavideostream_b200 as cvs
+    try:
+        return subprocess.run([CUOBJDUMP, "-sass", cvs.library_path()], capture_output=True, text=True, check=True).stdout
+    except (OSError, subprocess.CalledProcessError) as e:
+        pytest.skip(f"cuobjdump unavailable: {e}")
+
+
+def _function(name_regex: str) -> str:
+    blocks = re.split(r"(?=\n\s*Function : )", _sass())
+    hit = [b for b in blocks if re.search(r"Function : \S*" + name_regex, b)]
+    assert hit, f"no kernel matching {name_regex} in the library"
+    return hit[0]
+
+
+def test_library_is_sm_100a_only():
+    archs = set(re.findall(r"arch = (sm_\w+)", _sass()))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_stream_kernel_uses_tma_bulk_copies_and_byte_simd():
+    k = _function(r"k_streamILi0ELb0ELb1E")          # k_stream<0, false, true>
+    assert "UBLKCP" in k, "the frame ingest must be a TMA bulk copy (cp.async.bulk)"
+    assert "SYNCS" in k, "mbarrier (SYNCS.*) expected next to the bulk copy"
+    assert k.count("VABSDIFF4") >= 24, "one byte-SIMD absolute difference per word of the 96-byte chunk"
+    assert "REDUX" in k, "warp totals by redux.sync"
+    assert "HMMA" not in k and "UTC" not in k, "byte work: no tensor-core instructions expected"
+
+
+def test_no_kernel_spills_in_the_hot_variants():
+    # local-memory traffic (LDL/STL) in the default-mode stream kernels would mean register spills
+    for name in (r"k_streamILi0ELb0ELb1E", r"k_streamILi0ELb0ELb0E"):
+        k = _function(name)
+        assert not re.search(r"\b(LDL|STL)\b", k), f"{name} spills to local memory"
+
+
+def test_noise_filter_is_fma_in_fixed_order():
+    k = _function(r"k_conv_stripILi3ELb1E")
+    assert k.count("FFMA") == 8 * 36, "8 rows x 4 bytes x 9 taps, one FFMA each"
+    assert "F2I" not in k, "non-negative weights truncate with FADD.RZ, not F2I"
