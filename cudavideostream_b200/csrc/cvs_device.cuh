@@ -16,7 +16,7 @@ namespace cvs {
 __device__ __forceinline__ uint4 ldg_stream(const void *p)
 {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p));
     return v;
