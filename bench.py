@@ -154,7 +154,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "1080p_seq300_d1_10_50", "width": W, "height": H, "threshold": THR},
+            "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), T), "width": W, "height": H, "threshold": THR},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": vals[0]["sample"]},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -293,14 +293,14 @@ def ours(args):
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "1080p_seq300_d1_10_50", "width": W, "height": H, "threshold": THR,
+                "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), T), "width": W, "height": H, "threshold": THR,
                            "frames_per_sequence": T, "sequences_per_step": len(seqs), "streams_per_gpu": len(seqs),
                            "l2": "inputs larger than L2: 3 x %.2f GB device-resident frame sequences per step" % (T * N / 1e9),
                            "per_density": per_density},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                             "kernel": "cvs::k_stream<0,false,true> (one launch = one 300-frame sequence)",
+                             "kernel": "cvs::k_stream<0,false,%s> (one launch = one %d-frame sequence)" % ("true" if (N + 95) // 96 <= 512 * torch.cuda.get_device_properties(dev).multi_processor_count else "false", T),
                              "achieved_hbm_model": achieved_hbm, "frac_hbm_model": achieved_hbm / peak,
                              "note": "achieved = SURVEY 8(d) algorithmic bytes (2+6c)N+4 per frame / event-timed launch; "
                                      "hbm_model counts only bytes that must cross HBM when the reference stays on chip "
@@ -377,6 +377,7 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
 
 
 def main():
+    global W, H, N, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -387,7 +388,14 @@ def main():
     ap.add_argument("--e2e-ring", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--width", type=int, default=W, help="frame width (default: the 1080p headline workload)")
+    ap.add_argument("--height", type=int, default=H)
     args = ap.parse_args()
+    if (args.width, args.height) != (W, H):
+        # side workloads (e.g. BASELINE config 5's 3840x2160 streams); the headline stays 1080p
+        W, H = args.width, args.height
+        N = 3 * W * H
+        METRIC = "%dx%d frames/sec (diff+compact, %d-frame sequences at 1%%/10%%/50%% change density)" % (W, H, args.frames)
     if args.impl == "reference":
         return reference_arm(args)
     return ours(args)

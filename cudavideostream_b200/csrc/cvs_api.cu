@@ -176,6 +176,7 @@ struct cvs_stream_s {
     bool hi = false;
     uint32_t addc = 0;
     uint32_t debug = 0; // CVS_DEBUG_FLAGS (profiling experiments only)
+    int stages = 0;     // CVS_STAGES: ring depth override (0 = default)
     bool trace = false;
     cudaEvent_t ev_base = nullptr;
     bool push_payload = true; // CVS_PAYLOAD_PUSH=0 falls back to count round trip + copy engine
@@ -357,8 +358,10 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
     StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
-    // ring depth: see nstages in k_stream
-    const int smem_bytes = cvs::SmemLayout::total(refreg ? cvs::kStages : cvs::kStages - 1);
+    // ring depth: see nstages in k_stream (CVS_STAGES overrides it for experiments)
+    int nstages = refreg ? cvs::kStages : cvs::kStages - 1;
+    if (h->stages >= 2 && h->stages <= cvs::kStages) nstages = h->stages;
+    const int smem_bytes = cvs::SmemLayout::total(nstages);
     int &occ = h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
     if (occ == 0) { // first launch of this variant on this handle
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -393,6 +396,7 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.nchunks = h->nchunks;
         p.nseg = nseg;
         p.cps = cps;
+        p.nstages = (uint32_t)nstages;
         p.pos = d_pos + done;
         p.xs = d_xs + (size_t)done * cap;
         p.diff = d_diff + (size_t)done * cap;
@@ -516,6 +520,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     h->P16 = round_up(h->npix, 16);
     threshold_consts(cfg->threshold, h->hi, h->addc);
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
+    if (const char *sg = getenv("CVS_STAGES")) h->stages = atoi(sg);
     if (const char *pp = getenv("CVS_PAYLOAD_PUSH")) h->push_payload = atoi(pp) != 0;
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     memset(&h->weights, 0, sizeof h->weights);

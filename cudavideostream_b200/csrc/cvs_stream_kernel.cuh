@@ -56,6 +56,7 @@ namespace cvs {
 #endif
 constexpr int kThreads = CVS_STREAM_THREADS;           // threads per block
 constexpr int kWarps = kThreads / 32;
+constexpr int kWarpsPad = (kWarps + 3) / 4 * 4;       // stride of the per-warp total arrays
 constexpr int kBlocksPerSM = 512 / kThreads;          // 128 registers per thread fill the register file
 constexpr int kLook = (148 * kBlocksPerSM + kThreads - 1) / kThreads + 1; // look-back descriptors a thread may read
 constexpr int kGroupsPerThread = 2;
@@ -79,6 +80,7 @@ struct StreamParams {
     uint32_t nchunks;           // ceil(N / 96)
     uint32_t nseg;              // segments per frame
     uint32_t cps;               // chunks per block per segment (<= kThreads)
+    uint32_t nstages;           // ring stages in use (2..kStages); the launch pays SmemLayout::total(nstages)
     unsigned int *pos;          // [nframes]
     int *xs;                    // frame t at xs + t*cap
     uint8_t *diff;              // frame t at diff + t*cap
@@ -103,9 +105,9 @@ struct SmemLayout {
     static constexpr int kSdBytes = kWarpEntries + 16;
     static constexpr int lut = 0;                                          // 768 words
     static constexpr int hist = lut + 768 * 4;                             // 256 words
-    static constexpr int wtot = hist + 256 * 4;                            // 2 x kWarps words (by step parity)
-    static constexpr int red = wtot + 2 * kWarps * 4;                      // 2 x kWarps words
-    static constexpr int done = red + 2 * kWarps * 4;                      // kStages words
+    static constexpr int wtot = hist + 256 * 4;                            // 2 x kWarpsPad words (by step parity)
+    static constexpr int red = wtot + 2 * kWarpsPad * 4;                   // 2 x kWarpsPad words
+    static constexpr int done = red + 2 * kWarpsPad * 4;                   // kStages words
     static constexpr int bar = done + 8 * 4;                               // kStages mbarriers
     static constexpr int sxs = bar + 8 * 8;                                // kWarps * kXsHalves uint16
     static constexpr int sd = sxs + kWarps * kXsHalves * 2;                // kWarps * kSdBytes bytes
@@ -132,21 +134,19 @@ __device__ __forceinline__ void flush_warp(const uint16_t *sxs, const uint8_t *s
     int *xg = xs_out + (g0 - sh);
     uint8_t *dg = df_out + (g0 - sh);
     const uint32_t end = sh + n;
-    // quads [4i, 4i+4): full ones go out as one 16-byte + one 4-byte store, the (at most two) partial ones
-    // at the ends element by element
-    for (uint32_t e = 4 * lane; e < end; e += 128) {
-        if (e >= sh && e + 4 <= end) {
-            const uint2 h = *reinterpret_cast<const uint2 *>(sxs + e); // four 16-bit offsets
-            stg_stream(xg + e, make_uint4(wbase + (h.x & 0xffffu), wbase + (h.x >> 16), wbase + (h.y & 0xffffu), wbase + (h.y >> 16)));
-            stg_stream_u32(dg + e, *reinterpret_cast<const uint32_t *>(sd + e));
-        } else {
-#pragma unroll
-            for (uint32_t i = 0; i < 4; i++)
-                if (e + i >= sh && e + i < end) {
-                    stg_stream_u32(xg + e + i, wbase + sxs[e + i]);
-                    stg_stream_u8(dg + e + i, sd[e + i]);
-                }
-        }
+    // whole quads [4i, 4i+4) go out as one 16-byte + one 4-byte store per lane
+    const uint32_t q0 = (sh + 3u) & ~3u, q1 = end & ~3u;
+#pragma unroll 1
+    for (uint32_t e = q0 + 4 * lane; e < q1; e += 128) {
+        const uint2 h = *reinterpret_cast<const uint2 *>(sxs + e); // four 16-bit offsets
+        stg_stream(xg + e, make_uint4(wbase + (h.x & 0xffffu), wbase + (h.x >> 16), wbase + (h.y & 0xffffu), wbase + (h.y >> 16)));
+        stg_stream_u32(dg + e, *reinterpret_cast<const uint32_t *>(sd + e));
+    }
+    // the (at most three + three) entries before the first and after the last whole quad: one lane each
+    const uint32_t e1 = lane < 4 ? sh + lane : max(q1, q0) + (lane - 4);
+    if (lane < 8 && e1 < (lane < 4 ? min(q0, end) : end)) {
+        stg_stream_u32(xg + e1, wbase + sxs[e1]);
+        stg_stream_u8(dg + e1, sd[e1]);
     }
 }
 
@@ -171,25 +171,53 @@ __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_
     }
 }
 
+// base + scale * i as ONE 64-bit multiply-add (the plain pointer arithmetic costs an add and a carry add per store)
+__device__ __forceinline__ int *at_u32(int *base, uint32_t i)
+{
+    int *q;
+    asm("mad.wide.u32 %0, %1, 4, %2;" : "=l"(q) : "r"(i), "l"(base));
+    return q;
+}
+__device__ __forceinline__ uint8_t *at_u8(uint8_t *base, uint32_t i)
+{
+    uint8_t *q;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(q) : "r"(i), "l"(base));
+    return q;
+}
+
 // Dense warps (more entries than the staging window holds): the warp walks its 32 chunks one after the other
 // and handles each chunk with all lanes -- lane L owns bytes L, L+32 and L+64 of the chunk, finds its rank by a
-// popc over the broadcast change mask and stores straight to global memory.  Consecutive changed bytes land on
+// popc over the chunk's change mask and stores straight to global memory.  Consecutive changed bytes land on
 // consecutive ranks, so every store instruction writes one contiguous run (up to 128 B of indices).
+// The masks and the ranks of the first entry of each 32-byte third of every chunk are exchanged through `scratch`
+// (the warp's staging window, idle in a dense step): one broadcast 16-byte and one 8-byte shared load per chunk
+// instead of shuffles and popcounts.  CHECK = false when the warp's whole run fits the payload capacity.
+// This loop is the bulk of a dense frame's instructions.
+template <bool CHECK>
 __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
-                                          int *xs_out, uint8_t *df_out, uint32_t g_lane, size_t cap, uint32_t lane)
+                                          int *xs_out, uint8_t *df_out, uint32_t g_lane, uint32_t cap32, uint32_t lane,
+                                          uint32_t scratch)
 {
-    // 32-bit ranks and one-instruction bit tests: this loop is the bulk of a dense frame's instructions
-    const uint32_t cap32 = cap > 0xffffffffull ? 0xffffffffu : (uint32_t)cap;
+    {
+        const uint32_t r1 = g_lane + (uint32_t)__popc(m[0]), r2 = r1 + (uint32_t)__popc(m[1]);
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + 16 * lane), "r"(m[0]), "r"(m[1]), "r"(m[2]),
+                     "r"(g_lane) : "memory");
+        asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(scratch + 512 + 8 * lane), "r"(r1), "r"(r2) : "memory");
+    }
+    __syncwarp();
     const uint32_t lanebit = 1u << lane;
-    constexpr int kBatch = 4; // chunks in flight: their shuffles and shared loads are issued before any store
-    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t lt = lanebit - 1u;
+    constexpr int kBatch = 4; // chunks in flight: their shared loads are issued before any store
+#pragma unroll 1
     for (uint32_t S0 = 0; S0 < 32; S0 += kBatch) {
-        uint32_t sm[kBatch][kMaskWords], r[kBatch], v[kBatch][kMaskWords];
+        uint32_t sm[kBatch][kMaskWords], rk[kBatch][kMaskWords], v[kBatch][kMaskWords];
 #pragma unroll
         for (int i = 0; i < kBatch; i++) {
-#pragma unroll
-            for (int w = 0; w < kMaskWords; w++) sm[i][w] = __shfl_sync(0xffffffffu, m[w], S0 + i);
-            r[i] = __shfl_sync(0xffffffffu, g_lane, S0 + i); // global rank of the chunk's first entry
+            const uint4 a = lds128(scratch + 16 * (S0 + i));
+            uint32_t b0, b1;
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(scratch + 512 + 8 * (S0 + i)) : "memory");
+            sm[i][0] = a.x; sm[i][1] = a.y; sm[i][2] = a.z;
+            rk[i][0] = a.w; rk[i][1] = b0; rk[i][2] = b1;
         }
 #pragma unroll
         for (int i = 0; i < kBatch; i++)
@@ -198,15 +226,17 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
 #pragma unroll
         for (int i = 0; i < kBatch; i++) {
             const uint32_t cb = coff0 + (S0 + i) * kChunkBytes + lane;
-            uint32_t rr = r[i];
 #pragma unroll
             for (int w = 0; w < kMaskWords; w++) {
-                const uint32_t g = rr + (uint32_t)__popc(sm[i][w] & lt);
-                if ((sm[i][w] & lanebit) && g < cap32) {
-                    stg_stream_u32(xs_out + g, cb + 32 * w);
-                    stg_stream_u8(df_out + g, v[i][w]);
-                }
-                rr += (uint32_t)__popc(sm[i][w]);
+                const uint32_t g = rk[i][w] + (uint32_t)__popc(sm[i][w] & lt);
+                // both stores under one predicate (no branch around two instructions)
+                uint32_t on = sm[i][w] & lanebit;
+                if (CHECK && g >= cap32) on = 0;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+                             "@p st.global.cs.u32 [%1], %2;\n\t"
+                             "@p st.global.cs.u8 [%3], %4;\n\t}" ::"r"(on), "l"(at_u32(xs_out, g)), "r"(cb + 32 * w),
+                             "l"(at_u8(df_out, g)), "r"(v[i][w])
+                             : "memory");
             }
         }
     }
@@ -214,21 +244,17 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
 
 __device__ __forceinline__ uint32_t warp_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
 
-// sum of the first n and of all kWarps words at p (broadcast 16-byte shared loads, no shuffles)
-__device__ __forceinline__ void sum_warps(const uint32_t *p, uint32_t n, uint32_t &first_n, uint32_t &all)
+// sum of the first n and of all kWarps words at p: lane i reads word i, two warp reductions (REDUX)
+__device__ __forceinline__ void sum_warps(const uint32_t *p, uint32_t n, uint32_t lane, uint32_t &first_n, uint32_t &all)
 {
-    static_assert(kWarps % 4 == 0, "warp totals are read as 16-byte vectors");
-    first_n = 0; all = 0;
-#pragma unroll
-    for (int q4 = 0; q4 < kWarps / 4; q4++) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(p + 4 * q4);
-        const uint32_t v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if ((uint32_t)(4 * q4 + i) < n) first_n += v[i];
-            all += v[i];
-        }
-    }
+    static_assert(kWarps <= 32, "one lane per warp total");
+    const uint32_t v = lane < (uint32_t)kWarps ? p[lane] : 0u;
+    all = warp_add(v);
+    first_n = warp_add(lane < n ? v : 0u);
+}
+__device__ __forceinline__ uint32_t sum_warps(const uint32_t *p, uint32_t lane)
+{
+    return warp_add(lane < (uint32_t)kWarps ? p[lane] : 0u);
 }
 
 template <int MODE, bool HI, bool REFREG>
@@ -247,9 +273,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
     const uint32_t b = blockIdx.x, G = gridDim.x;
     const uint32_t N = p.nbytes;
     const uint32_t nsteps = (uint32_t)p.nframes * p.nseg;
-    // ring depth in use: all four stages when the reference lives in registers (measured +5 % at 1080p); three when
-    // it goes through L2 (a deeper prefetch measured 17 % slower at 3840x2160)
-    const uint32_t nstages = REFREG ? (uint32_t)kStages : (uint32_t)kStages - 1u;
+    // ring depth in use (chosen by the host, <= kStages): all four stages when the reference lives in registers
+    // (measured +5 % at 1080p); three when it goes through L2 (a deeper prefetch measured 17 % slower at 3840x2160)
+    const uint32_t nstages = p.nstages;
     constexpr bool kBinarize = (MODE == kModeBinarize || MODE == kModeBinarizeAvg);
     constexpr bool kGrayW = (MODE == kModeGrayWeighted || MODE == kModeBinarize);
     // this warp's staging window
@@ -269,12 +295,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
         off = (uint32_t)o;
         bytes = (uint32_t)(e - o);
     };
-    // one thread: refill the ring stage of step q
-    auto issue = [&](uint32_t q) {
-        uint32_t t = q / p.nseg, s = q - t * p.nseg, off, bytes;
+    // one thread: refill ring stage st with the slice of step q (st == q mod nstages, tracked by the callers: the
+    // ring depth is a launch parameter and a division per step would cost more than the rest of the bookkeeping)
+    auto issue = [&](uint32_t q, uint32_t st) {
+        // REFREG <=> one segment per frame
+        const uint32_t t = REFREG ? q : q / p.nseg, s = REFREG ? 0u : q - t * p.nseg;
+        uint32_t off, bytes;
         slice(s, off, bytes);
         if (bytes) {
-            const uint32_t st = q % nstages;
             const uint64_t pol = l2_policy_evict_first();
             // the stage was last written through the generic proxy (parked difference bytes)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -290,13 +318,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             mbar_init(bar_addr + 8 * i, 1);
             done[i] = 0;
         }
+        for (int i = 0; i < 2 * kWarpsPad; i++) wtot[i] = red[i] = 0;
         mbar_init_fence();
     }
     if (MODE == kModeHeat)
         for (uint32_t i = tid; i < 766; i += kThreads) slut[i] = p.heat_lut[i];
     __syncthreads();
     if (tid == 0)
-        for (uint32_t q = 0; q < nstages && q < nsteps; q++) issue(q);
+        for (uint32_t q = 0; q < nstages && q < nsteps; q++) issue(q, q);
 
     uint32_t r[kChunkWords];
     const uint64_t keep = l2_policy_evict_last();
@@ -341,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
     uint32_t b_wrank = 0, b_wexc = 0, b_wtotal = 0, b_total = 0, b_coff = 0, b_myaddr = 0, b_t = 0, b_s = 0;
     bool pending = false;
     uint32_t t = 0, s = 0; // frame and segment of step q
+    uint32_t st = 0, b_st = 0; // ring stage of step q / of step q-1
 
     for (uint32_t q = 0; q <= nsteps; q++) {
         const bool front = q < nsteps;
@@ -361,7 +391,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
         uint32_t m[kMaskWords] = {0, 0, 0};
         uint32_t cnt = 0, incl = 0, myaddr = 0;
         if (front) {
-            const uint32_t st = q % nstages;
             if (!REFREG) {
                 geometry(s);
                 load_ref(); // L2 hit; issued before the wait on the frame slice
@@ -451,14 +480,20 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             if (!(p.debug & 4u)) { // debug 4: skip the per-word pass (ingest-only experiment)
                 uint32_t dv[kChunkWords];
 #pragma unroll
-                for (int k = 0; k < kChunkWords; k++) {
-                    const uint32_t f = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
-                    // flag bits 7,15,23,31 -> adjacent bits 28..31 (all partial products land on distinct bits)
-                    const uint32_t nib = f * 0x00204081u;
-                    m[k >> 3] |= (nib >> (28 - 4 * (k & 7))) & (0xFu << (4 * (k & 7)));
+                for (int k = 0; k < kChunkWords; k += 2) {
+                    const uint32_t f0 = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
+                    const uint32_t f1 = changed80<HI>(absdiff4(c[k + 1], r[k + 1]), p.addc);
+                    // the eight flag bits of two words (7,15,23,31 and, shifted, 3,11,19,27) -> one byte of the change
+                    // mask: every partial product of the multiply lands on its own bit, and bits 32..39 of the product
+                    // are the flags in byte order
+                    const uint32_t g8 = __umulhi(f1 + (f0 >> 4), 0x20408100u);
+                    m[k >> 3] = __byte_perm(m[k >> 3], g8, ((k >> 1) & 3) == 0 ? 0x3214 : ((k >> 1) & 3) == 1 ? 0x3240
+                                                          : ((k >> 1) & 3) == 2 ? 0x3410 : 0x4210);
                     dv[k] = sub4(c[k], r[k]);
-                    const uint32_t fm = spread80(f);
-                    r[k] = (c[k] & fm) | (r[k] & ~fm);
+                    dv[k + 1] = sub4(c[k + 1], r[k + 1]);
+                    const uint32_t fm0 = spread80(f0), fm1 = spread80(f1);
+                    r[k] = (c[k] & fm0) | (r[k] & ~fm0);
+                    r[k + 1] = (c[k + 1] & fm1) | (r[k + 1] & ~fm1);
                 }
                 if (nv < (uint32_t)kChunkBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
 #pragma unroll
@@ -481,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             cnt = (uint32_t)__popc(m[0]) + (uint32_t)__popc(m[1]) + (uint32_t)__popc(m[2]);
             // only the warp total has to cross the barrier; the per-lane ranks are scanned after it
             const uint32_t wsum = warp_add(cnt);
-            if (lane == 0) wtot[(q & 1u) * kWarps + warp] = wsum;
+            if (lane == 0) wtot[(q & 1u) * kWarpsPad + warp] = wsum;
         }
 
         // ---- back half, part 2: the descriptors fetched at the top (retry in the rare case a predecessor
@@ -506,22 +541,21 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             if (has2) part += settle(pv2, prow - 1);
             // G <= kLook * kThreads is enforced by the host, so kLook reads per thread cover every predecessor
             part = warp_add(part);
-            if (lane == 0) red[(q & 1u) * kWarps + warp] = part;
+            if (lane == 0) red[(q & 1u) * kWarpsPad + warp] = part;
         }
 
         __syncthreads(); // the one barrier of a step: warp totals of step q, look-back partial sums of step q-1
 
         uint32_t total = 0, wexc = 0, wtotal = 0;
         if (front) {
-            sum_warps(wtot + (q & 1u) * kWarps, warp, wexc, total); // entries of the warps before this one / of the block
+            sum_warps(wtot + (q & 1u) * kWarpsPad, warp, lane, wexc, total); // entries of the warps before this one / of the block
             if (tid == 0) desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
             incl = warp_incl_scan(cnt, lane);
             wtotal = __shfl_sync(0xffffffffu, incl, 31); // entries of this warp in step q
         }
 
         if (pending) {
-            uint32_t base, unused;
-            sum_warps(red + (q & 1u) * kWarps, 0, unused, base);
+            const uint32_t base = sum_warps(red + (q & 1u) * kWarpsPad, lane);
             if (tid == 0) {
                 if (b == G - 1) {
                     desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
@@ -535,6 +569,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             //      lane store its own run of entries directly.  No other warp is involved either way.
             int *xs_out = p.xs + (size_t)b_t * p.cap;
             uint8_t *df_out = p.diff + (size_t)b_t * p.cap;
+            // opaque from here on: otherwise the compiler folds the frame offset into every store of the emission loops
+            // and recomputes it there in 64-bit arithmetic (nine instructions per store pair instead of two)
+            asm volatile("" : "+l"(xs_out), "+l"(df_out));
             const size_t g0 = (size_t)base + b_wexc; // global rank of this warp's first entry
             if (b_wtotal && !(p.debug & 2u)) {
                 if (b_wtotal <= (uint32_t)kWarpEntries) {
@@ -546,19 +583,24 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                 } else {
                     // chunk S of the warp starts 96*S bytes after lane 0's chunk (frame and ring stage alike); lane 0 holds a
                     // chunk of the frame whenever any lane of the warp does
-                    emit_coop(b_m, __shfl_sync(0xffffffffu, b_coff, 0), b_myaddr - lane * kChunkBytes, xs_out, df_out,
-                              (uint32_t)g0 + b_wrank, p.cap, lane);
+                    // 32-bit ranks: cap32 saturates, and a run that starts beyond it is dropped entry by entry
+                    const uint32_t cap32 = p.cap > 0xffffffffull ? 0xffffffffu : (uint32_t)p.cap;
+                    const uint32_t wb = __shfl_sync(0xffffffffu, b_coff, 0), dv0 = b_myaddr - lane * kChunkBytes;
+                    if (g0 + b_wtotal <= (size_t)cap32)
+                        emit_coop<false>(b_m, wb, dv0, xs_out, df_out, (uint32_t)g0 + b_wrank, cap32, lane, smem_u32(sxs));
+                    else
+                        emit_coop<true>(b_m, wb, dv0, xs_out, df_out, (uint32_t)g0 + b_wrank, cap32, lane, smem_u32(sxs));
                 }
             }
             // ---- this warp is done with the ring stage of step q-1 (pixels consumed before the barrier of
             //      that step, parked bytes emitted above); the last warp to get here refills the stage
             __syncwarp();
             if (lane == 0) {
-                const uint32_t stq = (q - 1) % nstages;
+                const uint32_t stq = b_st;
                 __threadfence_block();
                 if (atomicAdd(&done[stq], 1u) == (uint32_t)kWarps - 1u) {
                     done[stq] = 0;
-                    if (q - 1 + nstages < nsteps) issue(q - 1 + nstages);
+                    if (q - 1 + nstages < nsteps) issue(q - 1 + nstages, stq);
                 }
             }
         }
@@ -575,6 +617,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             b_coff = coff; b_myaddr = myaddr; b_t = t; b_s = s;
             pending = true;
             if (++s == p.nseg) { s = 0; ++t; }
+            b_st = st;
+            if (++st == nstages) st = 0;
         } else {
             pending = false;
         }
