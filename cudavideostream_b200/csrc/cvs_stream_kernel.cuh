@@ -327,6 +327,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
     if (tid == 0)
         for (uint32_t q = 0; q < nstages && q < nsteps; q++) issue(q, q);
 
+    // Bank-conflict-free 16-byte shared accesses.  Chunks are 96 B apart, so with every lane on the same vector of
+    // its chunk lanes L and L+4 of a quarter-warp hit the same banks (6L mod 8 takes four values).  Lanes with bit 2
+    // set therefore keep their two 48-byte pixel groups in SWAPPED order in registers ("slot" order): slot vector v
+    // of such a lane is vector (v+3) mod 6 of the chunk, which lands on the four odd bank groups.  Only the change
+    // mask has to be put back into byte order; every address below goes through voff().
+    const uint32_t sw = ((lane >> 2) & 1u) * (uint32_t)kGroupBytes; // 0 or 48
+    auto voff = [&](int v) -> uint32_t { return v < 3 ? 16u * v + sw : 16u * v - sw; }; // chunk offset of slot vector v
     uint32_t r[kChunkWords];
     const uint64_t keep = l2_policy_evict_last();
     bool dirty = false;
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
         if (nv) {
 #pragma unroll
             for (int v = 0; v < kChunkWords / 4; v++) {
-                uint4 a = ldg_keep(p.ref + coff + 16 * v, keep);
+                uint4 a = ldg_keep(p.ref + coff + voff(v), keep);
                 r[4 * v] = a.x; r[4 * v + 1] = a.y; r[4 * v + 2] = a.z; r[4 * v + 3] = a.w;
             }
         } else {
@@ -355,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
     auto store_ref = [&]() {
 #pragma unroll
         for (int v = 0; v < kChunkWords / 4; v++)
-            stg_keep(p.ref + coff + 16 * v, make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]), keep);
+            stg_keep(p.ref + coff + voff(v), make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]), keep);
     };
 
     geometry(0);
@@ -416,13 +423,13 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             if (nv) {
 #pragma unroll
                 for (int v = 0; v < kChunkWords / 4; v++) {
-                    uint4 x = lds128(myaddr + 16 * v);
+                    uint4 x = lds128(myaddr + voff(v));
                     c[4 * v] = x.x; c[4 * v + 1] = x.y; c[4 * v + 2] = x.z; c[4 * v + 3] = x.w;
                 }
                 if (nv < (uint32_t)kChunkBytes) { // the chunk that holds the end of the frame: bytes past N never differ
 #pragma unroll
                     for (int k = 0; k < kChunkWords; k++) {
-                        const int vb = (int)nv - 4 * k;
+                        const int vb = (int)nv - (int)(voff(k >> 2) + 4 * (k & 3)); // valid bytes from this slot word on
                         const uint32_t vm = vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << (8 * vb)) - 1u));
                         c[k] = (c[k] & vm) | (r[k] & ~vm);
                     }
@@ -436,8 +443,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             if (MODE != kModeNone && nv) {
 #pragma unroll
                 for (int g = 0; g < kGroupsPerThread; g++) {
-                    const uint32_t goff = coff + g * kGroupBytes;
-                    const uint32_t gnv = nv > (uint32_t)(g * kGroupBytes) ? min(nv - g * kGroupBytes, (uint32_t)kGroupBytes) : 0u;
+                    const uint32_t gb = sw ? (uint32_t)(1 - g) * kGroupBytes : (uint32_t)g * kGroupBytes; // slot group -> chunk
+                    const uint32_t goff = coff + gb;
+                    const uint32_t gnv = nv > gb ? min(nv - gb, (uint32_t)kGroupBytes) : 0u;
                     if (gnv == 0) continue;
                     uint32_t cg[kGroupWords], rg[kGroupWords], o[kGroupWords];
 #pragma unroll
@@ -495,6 +503,11 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     r[k] = (c[k] & fm0) | (r[k] & ~fm0);
                     r[k + 1] = (c[k + 1] & fm1) | (r[k + 1] & ~fm1);
                 }
+                if (sw) { // slot order -> byte order: rotate the 96-bit mask by 48
+                    const uint32_t n0 = __funnelshift_r(m[1], m[2], 16), n1 = __funnelshift_r(m[2], m[0], 16),
+                                   n2 = __funnelshift_r(m[0], m[1], 16);
+                    m[0] = n0; m[1] = n1; m[2] = n2;
+                }
                 if (nv < (uint32_t)kChunkBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
 #pragma unroll
                     for (int w = 0; w < kMaskWords; w++) {
@@ -506,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     // park the difference bytes in this thread's own 96 bytes of the stage
 #pragma unroll
                     for (int v = 0; v < kChunkWords / 4; v++)
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + 16 * v), "r"(dv[4 * v]),
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(v)), "r"(dv[4 * v]),
                                      "r"(dv[4 * v + 1]), "r"(dv[4 * v + 2]), "r"(dv[4 * v + 3])
                                      : "memory");
                     if (REFREG) dirty = true;
