@@ -207,7 +207,10 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
     __syncwarp();
     const uint32_t lanebit = 1u << lane;
     const uint32_t lt = lanebit - 1u;
-    constexpr int kBatch = 4; // chunks in flight: their shared loads are issued before any store
+#ifndef CVS_COOP_BATCH
+#define CVS_COOP_BATCH 2
+#endif
+    constexpr int kBatch = CVS_COOP_BATCH; // chunks in flight: their shared loads are issued before any store
 #pragma unroll 1
     for (uint32_t S0 = 0; S0 < 32; S0 += kBatch) {
         uint32_t sm[kBatch][kMaskWords], rk[kBatch][kMaskWords], v[kBatch][kMaskWords];
