@@ -147,14 +147,15 @@ def reference_arm(args):
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_run(2.0, threads)
     for _ in range(args.steps):
-        vals.append(cpu_run(max(3.0, 20.0 / args.steps), threads))
+        vals.append(cpu_run(max(args.ref_seconds / 7.0, args.ref_seconds / args.steps), threads))
     frames = sum(v["frames"] for v in vals)
     sec = sum(v["seconds"] for v in vals)
     value = frames / sec
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), T), "width": W, "height": H, "threshold": THR},
+            "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), args.frames),
+                       "width": W, "height": H, "threshold": THR},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": vals[0]["sample"]},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -285,7 +286,7 @@ def ours(args):
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
             # ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (mean of the three densities) x frames per launch
-            traffic = json.load(fh)["dram_bytes_per_frame_mean"] * T
+            traffic = json.load(fh)["dram_bytes_per_frame_mean"] * T if (W, H) == (1920, 1080) else None
     except Exception:
         pass
 
@@ -388,6 +389,7 @@ def main():
     ap.add_argument("--e2e-ring", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: CPU seconds over all steps")
     ap.add_argument("--width", type=int, default=W, help="frame width (default: the 1080p headline workload)")
     ap.add_argument("--height", type=int, default=H)
     args = ap.parse_args()

@@ -97,3 +97,20 @@ def test_job_reduction_world_size_2_gloo():
         assert elapsed == 1.0          # max over ranks
         assert frames == 1500          # sum over ranks
         assert launches == 5
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) works without a GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-seconds", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "frames/s" and j["value"] > 0
+    assert j["config"]["workload"] == "1080p_seq300_d1_10_50"
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["cpu_baseline"]["kind"] in ("port", "reference")
