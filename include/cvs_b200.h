@@ -111,7 +111,10 @@ cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *t
                       unsigned int *pos, int *xs, uint64_t *ticket);
 cvs_status cvs_wait(cvs_handle h, uint64_t ticket);
 /* cvs_submit with the payload bytes written to a separate buffer instead of over the head of the input
- * frame (which is then left untouched): for callers that keep captured frames in a pinned ring. */
+ * frame (which is then left untouched): for callers that keep captured frames in a pinned ring.
+ * diff_out (capacity N bytes) and xs (capacity N ints) hold the payload in [0, *pos); what lies past *pos is
+ * unspecified on this entry point: the copy engine fetches a predicted number of entries right behind the
+ * count instead of waiting for the host to read it (CVS_EGRESS_SPECULATE=0 turns that off). */
 cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show,
                          const char *text, unsigned int *pos, int *xs, uint64_t *ticket);
 

@@ -179,6 +179,57 @@ def test_submit_wait_pipeline(cvs, oracle):
     s.close()
 
 
+@pytest.mark.parametrize("speculate", ["1", "0"])
+def test_submit_io_jumping_density(cvs, oracle, speculate, monkeypatch):
+    """cvs_submit_io keeps the input frame intact and copies a PREDICTED payload size behind the count: frames whose
+    count jumps far above / falls far below the prediction must still deliver exactly [0, pos)."""
+    monkeypatch.setenv("CVS_EGRESS_SPECULATE", speculate)
+    w, h = 320, 180
+    n = 3 * w * h
+    rng = np.random.default_rng(77)
+    base = rng.integers(0, 256, n, dtype=np.uint8)
+    # the predicted copy is used when the previous count lies in [N/64, N/4]: 0.05 -> 0.9 under-predicts (remainder
+    # copy), 0.1 -> 0.0 over-predicts, 0.05 -> 0.06 is the normal case
+    dens = [0.001, 0.05, 0.9, 0.0, 0.1, 0.0, 0.3, 1.0, 0.05, 0.06, 0.2, 0.002, 0.6, 0.05, 0.0, 0.45]
+    frames, cur = [], base.copy()
+    for d in dens:
+        nxt = cur.copy()
+        idx = np.flatnonzero(rng.random(n) < d)
+        nxt[idx] = (nxt[idx].astype(np.int64) + rng.integers(40, 200, idx.size)).astype(np.uint8)
+        frames.append(nxt)
+        cur = nxt
+    s = cvs.Stream(w, h, base)
+    oc = oracle.OracleCore(w, h, base)
+    ring = cvs.alloc_host(len(frames) * n)
+    for t, f in enumerate(frames):
+        ring.array()[t * n:(t + 1) * n] = f
+    bufs = [(cvs.alloc_host(n + 32), cvs.alloc_host(4 * n + 32), (C.c_uint * 1)()) for _ in range(4)]
+
+    def check(tt):
+        ofb, oxb, opb = bufs[tt % 4]
+        opos, oxs, odiff, _, _ = oc.exec_core(frames[tt])
+        assert opb[0] == opos, f"frame {tt}: pos {opb[0]} != {opos}"
+        assert np.array_equal(ofb.array()[:opos], odiff), f"frame {tt}: diff bytes differ"
+        assert np.array_equal(oxb.array(np.int32)[:opos], oxs), f"frame {tt}: xs differ"
+
+    tickets = []
+    for t in range(len(frames)):
+        if len(tickets) == 4:
+            tk, tt = tickets.pop(0)
+            s.wait(tk)
+            check(tt)
+        fb, xb, pb = bufs[t % 4]
+        tickets.append((s.submit_io_raw(ring.ptr + t * n, fb.ptr, None, "", C.addressof(pb), xb.ptr), t))
+    for tk, tt in tickets:
+        s.wait(tk)
+        check(tt)
+    # the captured frames were not touched
+    for t, f in enumerate(frames):
+        assert np.array_equal(ring.array()[t * n:(t + 1) * n], f)
+    assert np.array_equal(s.reference(), oc.reference())
+    s.close()
+
+
 def test_golden_real_camera_crop(cvs):
     # 128x72 crop of the reference's own fixture frames f1.jpg/f2.jpg with the oracle payload recorded in the
     # build container (tests/golden/make_golden.py)
