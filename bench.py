@@ -137,6 +137,20 @@ def cpu_run(target_seconds: float, threads: int):
                       f"workload, oracle/cvs_oracle.c orc_diff_compact -O2, frames in host RAM"}
 
 
+def cpu_single_thread(frames_per_density: int = 4):
+    """the reference's compute runs on ONE thread (server.cpp:70-146) and its Makefile ships
+    -O0 (server/Makefile:13).  A few frames per density of the same workload, one thread, -O2 and -O0 builds."""
+    from oracle import oracle as orc
+    orc.build()
+    out = {}
+    for name, o0 in (("O2", False), ("O0", True)):
+        sec = 0.0
+        for b, r in cpu_rings():
+            sec += orc.bench_diff_compact(r, b, THR, frames_per_density, 1, o0=o0)[0]
+        out["frames_per_s_1thread_" + name] = 3 * frames_per_density / sec
+    return out
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -157,7 +171,7 @@ def reference_arm(args):
             "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), args.frames),
                        "width": W, "height": H, "threshold": THR},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": vals[0]["sample"]},
+                             "sample": vals[0]["sample"], "single_thread": cpu_single_thread()},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
@@ -310,6 +324,7 @@ def ours(args):
         if world == 1 and not args.no_cpu:
             cb = cpu_run(args.cpu_seconds, os.cpu_count() or 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["single_thread"] = cpu_single_thread()
         print(json.dumps(line), flush=True)
     for q in seqs:
         q["stream"].close()
