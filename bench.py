@@ -313,7 +313,7 @@ def ours(args):
                            "l2": "inputs larger than L2: 3 x %.2f GB device-resident frame sequences per step" % (T * N / 1e9),
                            "per_density": per_density},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic,
+                             "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
                              "kernel": "cvs::k_stream<0,false,%s> (one launch = one %d-frame sequence)" % ("true" if (N + 95) // 96 <= 512 * torch.cuda.get_device_properties(dev).multi_processor_count else "false", T),
                              "achieved_hbm_model": achieved_hbm, "frac_hbm_model": achieved_hbm / peak,
