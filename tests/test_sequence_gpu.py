@@ -237,6 +237,46 @@ def test_no_write_outside_the_buffers(cvs, w, h, mode):
     s.close()
 
 
+@pytest.mark.parametrize("density,cap", [(1.0, 1000), (0.5, 4096), (0.05, 256), (1.0, 4)])
+def test_truncated_payload_stays_inside_capacity(cvs, oracle, density, cap):
+    # a frame with more changed bytes than the payload capacity: the first `cap` entries are delivered, the true count
+    # is reported with CVS_ERR_CAPACITY, and nothing is written past the capacity (dense and sparse emission paths)
+    import torch
+    G = 4096
+    w, h, nframes = 250, 130, 3
+    n = 3 * w * h
+    stride = (n + 15) // 16 * 16
+    base, frames = random_sequence(w, h, nframes, density, seed=9)
+
+    def guarded(nbytes, dtype=torch.uint8):
+        raw = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+        return raw, raw[G:G + nbytes].view(dtype)
+
+    d_frames = torch.zeros(nframes * stride, dtype=torch.uint8, device="cuda")
+    for t in range(nframes):
+        d_frames[t * stride: t * stride + n] = torch.from_numpy(frames[t]).cuda()
+    raw_p, d_pos = guarded(4 * nframes, torch.int32)
+    raw_x, d_xs = guarded(4 * nframes * cap, torch.int32)
+    raw_d, d_diff = guarded(nframes * cap)
+    s = cvs.Stream(w, h, base)
+    oc = oracle.OracleCore(w, h, base)
+    s.run_sequence_device(d_frames.data_ptr(), stride, nframes, d_pos.data_ptr(), d_xs.data_ptr(), d_diff.data_ptr(),
+                          cap, 0, stride, cuda_stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    with pytest.raises(cvs.CVSError) as e:
+        s.sequence_status()
+    assert e.value.status == 5  # CVS_ERR_CAPACITY
+    for raw in (raw_p, raw_x, raw_d):
+        assert bool((raw[:G] == 0xA5).all()) and bool((raw[-G:] == 0xA5).all())
+    for t in range(nframes):
+        opos, oxs, odiff, _, _ = oc.exec_core(frames[t])
+        assert int(d_pos[t]) == opos and opos > cap
+        assert np.array_equal(d_xs[t * cap:(t + 1) * cap].cpu().numpy(), oxs[:cap]), f"frame {t}"
+        assert np.array_equal(d_diff[t * cap:(t + 1) * cap].cpu().numpy(), odiff[:cap]), f"frame {t}"
+    assert np.array_equal(s.reference(), oc.reference())  # the feedback does not depend on the capacity
+    s.close()
+
+
 @pytest.mark.parametrize("levels", [[0], [1], [100], [255], [10, 200], [200, 10], [50, 50, 90], [0, 255, 255]])
 def test_threshold_quirks_on_gpu(cvs, oracle, levels):
     # histograms that hit the corners of the two-max loop (server.cpp:108-127): arg-max at bin 0 (isec = -1), ties,
