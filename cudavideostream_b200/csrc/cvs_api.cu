@@ -278,13 +278,21 @@ cvs_status launch_conv(const uint8_t *in, uint8_t *out, int width, int height, s
         float sum = 0.f;
         for (int i = 0; i < K * K; i++) { nonneg = nonneg && w.k[i] >= 0.f; sum += w.k[i]; }
         nonneg = nonneg && sum <= 16384.f;
-        dim3 block(128), grid((rowbytes / 4 + 127) / 128, (height + cvs::kConvRows - 1) / cvs::kConvRows, nframes);
-        if (K == 3) {
-            if (nonneg) cvs::k_conv_strip<3, true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
-            else cvs::k_conv_strip<3, false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        // two words per thread when every row and frame starts 8-byte aligned (K = 3 only: the K = 5 window would not
+        // fit in registers)
+        const bool wide = K == 3 && rowbytes % 8 == 0 && in_stride % 8 == 0 && out_stride % 8 == 0 &&
+                          (uintptr_t)in % 8 == 0 && (uintptr_t)out % 8 == 0;
+        const int wb = wide ? 2 : 1;
+        dim3 block(128), grid((rowbytes / (4 * wb) + 127) / 128, (height + cvs::kConvRows - 1) / cvs::kConvRows, nframes);
+        if (wide) {
+            if (nonneg) cvs::k_conv_strip<3, true, 2><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            else cvs::k_conv_strip<3, false, 2><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+        } else if (K == 3) {
+            if (nonneg) cvs::k_conv_strip<3, true, 1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            else cvs::k_conv_strip<3, false, 1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
         } else {
-            if (nonneg) cvs::k_conv_strip<5, true><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
-            else cvs::k_conv_strip<5, false><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            if (nonneg) cvs::k_conv_strip<5, true, 1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
+            else cvs::k_conv_strip<5, false, 1><<<grid, block, 0, st>>>(in, out, width, height, in_stride, out_stride, w);
         }
     } else if (fast) {
         dim3 block(256), grid((rowbytes / 4 + 255) / 256, height, nframes);

@@ -88,21 +88,22 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) // b: compi
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)b)) - 8388608.0f;
 }
 
-template <int K, bool NONNEG>
+template <int K, bool NONNEG, int WB>
 __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int width,
                                                     int height, size_t in_stride, size_t out_stride,
                                                     const __grid_constant__ ConvWeights w)
 {
-    constexpr int R = K / 2, HALO = 3 * R, WL = (HALO + 3) / 4, NW = 1 + 2 * WL, NF = 4 + 2 * HALO;
+    // a thread produces WB words (4*WB bytes) x kConvRows rows; WB = 2 halves the halo conversions per output byte
+    constexpr int R = K / 2, HALO = 3 * R, WL = (HALO + 3) / 4, NW = WB + 2 * WL, NB = 4 * WB, NF = NB + 2 * HALO;
     const int rowbytes = 3 * width;
     const int wordsperrow = rowbytes >> 2;
-    const int xw = blockIdx.x * blockDim.x + threadIdx.x; // word column
+    const int xw = (blockIdx.x * blockDim.x + threadIdx.x) * WB; // first word column of this thread
     const int row0 = blockIdx.y * kConvRows;
     if (xw >= wordsperrow) return;
     const uint8_t *fin = in + (size_t)blockIdx.z * in_stride;
     uint8_t *fout = out + (size_t)blockIdx.z * out_stride;
 
-    float f[K][NF]; // window: bytes x-HALO .. x+3+HALO of K consecutive input rows
+    float f[K][NF]; // window: bytes x-HALO .. x+NB-1+HALO of K consecutive input rows
     auto load_row = [&](int rr, float (&dst)[NF]) {
         uint32_t wd[NW];
 #pragma unroll
@@ -125,24 +126,32 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
         const int row = row0 + r;
         if (row >= height) break;
         load_row(row + R, f[(r + K - 1) % K]);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[NB];
+#pragma unroll
+        for (int o = 0; o < NB; o++) acc[o] = 0.f;
 #pragma unroll
         for (int i = 0; i < K; i++)
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const float kw = w.k[i * K + j];
 #pragma unroll
-                for (int o = 0; o < 4; o++) acc[o] = __fmaf_rn(kw, f[(r + i) % K][o + 3 * j], acc[o]);
+                for (int o = 0; o < NB; o++) acc[o] = __fmaf_rn(kw, f[(r + i) % K][o + 3 * j], acc[o]);
             }
-        uint32_t pk;
-        if (NONNEG) {
-            const uint32_t b0 = __float_as_uint(__fadd_rz(acc[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rz(acc[1], 8388608.0f)),
-                           b2 = __float_as_uint(__fadd_rz(acc[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rz(acc[3], 8388608.0f));
-            pk = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-        } else {
-            pk = trunc_u8(acc[0]) | (trunc_u8(acc[1]) << 8) | (trunc_u8(acc[2]) << 16) | (trunc_u8(acc[3]) << 24);
+        uint32_t pk[WB];
+#pragma unroll
+        for (int q = 0; q < WB; q++) {
+            const float *a = acc + 4 * q;
+            if (NONNEG) {
+                const uint32_t b0 = __float_as_uint(__fadd_rz(a[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rz(a[1], 8388608.0f)),
+                               b2 = __float_as_uint(__fadd_rz(a[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rz(a[3], 8388608.0f));
+                pk[q] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+            } else {
+                pk[q] = trunc_u8(a[0]) | (trunc_u8(a[1]) << 8) | (trunc_u8(a[2]) << 16) | (trunc_u8(a[3]) << 24);
+            }
         }
-        reinterpret_cast<uint32_t *>(fout + (size_t)row * rowbytes)[xw] = pk;
+        uint32_t *dst = reinterpret_cast<uint32_t *>(fout + (size_t)row * rowbytes) + xw;
+        if (WB == 2) *reinterpret_cast<uint2 *>(dst) = make_uint2(pk[0], pk[WB - 1]); // host guarantees 8-byte alignment
+        else dst[0] = pk[0];
     }
 }
 

@@ -47,6 +47,8 @@ def test_no_kernel_spills_in_the_hot_variants():
 
 
 def test_noise_filter_is_fma_in_fixed_order():
-    k = _function(r"k_conv_stripILi3ELb1E")
-    assert k.count("FFMA") == 8 * 36, "8 rows x 4 bytes x 9 taps, one FFMA each"
-    assert "F2I" not in k, "non-negative weights truncate with FADD.RZ, not F2I"
+    for wb in (1, 2):   # k_conv_strip<3, true, WB>: WB words (4*WB bytes) per thread
+        k = _function(r"k_conv_stripILi3ELb1ELi%dE" % wb)
+        assert k.count("FFMA") == 8 * 36 * wb, "8 rows x 4*WB bytes x 9 taps, one FFMA each"
+        assert "F2I" not in k, "non-negative weights truncate with FADD.RZ, not F2I"
+        assert not re.search(r"\b(LDL|STL)\b", k), "the row window must stay in registers"
