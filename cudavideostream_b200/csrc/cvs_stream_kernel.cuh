@@ -18,26 +18,30 @@
 //     A frame is covered in nseg passes ("segments") of G*cps chunks; in segment s block b owns the cps
 //     consecutive chunks starting at (s*G + b)*cps and thread i of the block owns chunk i of that
 //     slice -- the SAME bytes in every frame.  One (frame, segment) pair is a "step";
-//   * ingest: a block streams its slice of the coming steps into a 3-stage shared-memory ring with
-//     1-D bulk copies (TMA engine, cp.async.bulk + mbarrier, L2 evict-first): every byte of a frame
-//     crosses HBM -> SM exactly once, as 24 KB contiguous requests, and each thread picks its 32
-//     whole pixels out of shared memory with six LDS.128;
+//   * ingest: a block streams its slice of the coming steps into a shared-memory ring (4 stages of 48 KB
+//     when the reference lives in registers, 3 otherwise) with 1-D bulk copies (TMA engine,
+//     cp.async.bulk + mbarrier, L2 evict-first): every byte of a frame crosses HBM -> SM exactly once,
+//     as one contiguous request per slice (42 KB at 1080p), and each thread picks its 32 whole pixels
+//     out of shared memory with six conflict-free LDS.128 (half the lanes keep their two pixel groups
+//     in swapped order, see voff());
 //   * reference: when a frame fits one segment (1080p on 148 SMs) the thread's 96 reference bytes
 //     live in registers for the whole sequence (REFREG): HBM never sees the reference between the
 //     first frame and the last.  Otherwise each thread reloads / rewrites its own bytes with L2
 //     evict-last accesses (the reference frame stays L2 resident; same thread, same address, so no
 //     cross-thread hazard exists);
-//   * one pass over the 24 words of a chunk produces, per word: byte-SIMD |cur-ref| > T flags, the
-//     4-bit change nibble (one multiply gathers the four flag bits) merged into a 96-bit change mask,
+//   * one pass over the 24 words of a chunk produces, per word: byte-SIMD |cur-ref| > T flags (the
+//     eight flags of two words are gathered into one byte of the 96-bit change mask by ONE multiply),
 //     the difference bytes cur-ref (parked in the thread's own 96 bytes of the ring stage) and the
 //     updated reference (negative feedback).  popc of the mask is the thread's entry count;
-//   * compaction: warp shuffle scan + one block scan (the only block-wide barrier of a step);
+//   * compaction: warp totals by REDUX, one block barrier per step, per-lane ranks by a shuffle scan;
 //     cross-block offsets by a one-round decoupled look-back: each block publishes
 //     (epoch<<32 | count) for the step and sums the descriptors of its predecessors, each read by
 //     its own thread; the running total of earlier segments of the frame travels in one extra
-//     descriptor.  Each WARP then walks the set bits of its lanes' masks, stages (index, value) in
+//     descriptor.  A sparse WARP then walks the set bits of its lanes' masks, stages (index, value) in
 //     its own shared-memory window in rank order and flushes it with 16-byte (xs) / 4-byte (diff)
-//     coalesced streaming stores -- warps drift apart freely, the last one to finish refills the stage;
+//     coalesced streaming stores; a dense warp (more entries than the window holds) walks its chunks
+//     with all lanes and stores contiguous runs straight to global memory (emit_coop) -- warps drift
+//     apart freely, the last one to finish refills the stage;
 //   * display filter MODE (heat map, red maps, grayscale, binarisation pass 1) is computed from the
 //     same registers and written with 16-byte streaming stores;
 //   * the step loop is software-pipelined: while a block runs the front half of step q (ingest ...
