@@ -170,9 +170,18 @@ __device__ __forceinline__ uint32_t absdiff4(uint32_t a, uint32_t b) { return __
 
 // per-byte a - b (mod 256): the payload value df & 0xFF of test.cu:566.  Bit 7 of every byte lane of the
 // minuend is forced on and cleared in the subtrahend so no borrow crosses a lane; the true bit 7 is patched in.
+// ONE_LOP: the final t ^ x ^ 0x80808080 forced into one three-input logic op (left to itself the compiler emits two:
+// 6 instead of 5 instructions per word).  Costs registers where they are scarce, so the caller chooses.
+template <bool ONE_LOP>
 __device__ __forceinline__ uint32_t sub4(uint32_t a, uint32_t b)
 {
     const uint32_t t = (a | 0x80808080u) - (b & 0x7f7f7f7fu);
+    if (ONE_LOP) { // t ^ ((a ^ b) & H) ^ H with the last two xors as one three-input op
+        const uint32_t x = (a ^ b) & 0x80808080u;
+        uint32_t z;
+        asm("lop3.b32 %0, %1, %2, 0x80808080, 0x96;" : "=r"(z) : "r"(t), "r"(x));
+        return z;
+    }
     return t ^ ((a ^ ~b) & 0x80808080u);
 }
 

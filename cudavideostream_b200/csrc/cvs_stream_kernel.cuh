@@ -62,7 +62,9 @@ constexpr int kThreads = CVS_STREAM_THREADS;           // threads per block
 constexpr int kWarps = kThreads / 32;
 constexpr int kWarpsPad = (kWarps + 3) / 4 * 4;       // stride of the per-warp total arrays
 constexpr int kBlocksPerSM = 512 / kThreads;          // 128 registers per thread fill the register file
-constexpr int kLook = (148 * kBlocksPerSM + kThreads - 1) / kThreads + 1; // look-back descriptors a thread may read
+// look-back descriptors a thread may read: one per kThreads blocks of a B200-sized grid (the host clamps the grid
+// to kLook * kThreads blocks on a larger device)
+constexpr int kLook = (148 * kBlocksPerSM + kThreads - 1) / kThreads;
 constexpr int kGroupsPerThread = 2;
 constexpr int kChunkBytes = kGroupsPerThread * kGroupBytes;   // 96
 constexpr int kChunkWords = kChunkBytes / 4;                  // 24
@@ -394,7 +396,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
         unsigned long long pv[kLook], pv2 = 0;
         const unsigned long long *prow = p.desc + (size_t)(q ? q - 1 : 0) * (G + 1);
         const bool look = pending && !(p.debug & 1u);
-        const bool has2 = look && b_s > 0 && tid == (b % kThreads);
+        // REFREG <=> one segment per frame: no running total of earlier segments, s stays 0 (compile-time)
+        const bool has2 = !REFREG && look && b_s > 0 && tid == (b % kThreads);
 #pragma unroll
         for (int i = 0; i < kLook; i++) {
             pv[i] = 0;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     uint4 x = lds128(myaddr + voff(v));
                     c[4 * v] = x.x; c[4 * v + 1] = x.y; c[4 * v + 2] = x.z; c[4 * v + 3] = x.w;
                 }
-                if (nv < (uint32_t)kChunkBytes) { // the chunk that holds the end of the frame: bytes past N never differ
+                if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) { // the chunk that holds the end of the frame: bytes past N never differ
 #pragma unroll
                     for (int k = 0; k < kChunkWords; k++) {
                         const int vb = (int)nv - (int)(voff(k >> 2) + 4 * (k & 3)); // valid bytes from this slot word on
@@ -493,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             // ---- 3. one pass: flags -> 96-bit change mask, difference bytes, negative feedback
             //         reference := changed ? current : reference                      (test.cu:565-570)
             if (!(p.debug & 4u)) { // debug 4: skip the per-word pass (ingest-only experiment)
-                uint32_t dv[kChunkWords];
+                uint32_t dv[4];
 #pragma unroll
                 for (int k = 0; k < kChunkWords; k += 2) {
                     const uint32_t f0 = changed80<HI>(absdiff4(c[k], r[k]), p.addc);
@@ -504,8 +507,14 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     const uint32_t g8 = __umulhi(f1 + (f0 >> 4), 0x20408100u);
                     m[k >> 3] = __byte_perm(m[k >> 3], g8, ((k >> 1) & 3) == 0 ? 0x3214 : ((k >> 1) & 3) == 1 ? 0x3240
                                                           : ((k >> 1) & 3) == 2 ? 0x3410 : 0x4210);
-                    dv[k] = sub4(c[k], r[k]);
-                    dv[k + 1] = sub4(c[k + 1], r[k + 1]);
+                    dv[k & 3] = sub4<true>(c[k], r[k]);
+                    dv[(k & 3) + 1] = sub4<true>(c[k + 1], r[k + 1]);
+                    if ((k & 3) == 2) // park the difference bytes of this 16-byte vector in the thread's own 96 bytes of the
+                                      // stage right away (needed only if the chunk has entries, but 24 live registers cost more
+                                      // than six unconditional shared stores)
+                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(k >> 2)), "r"(dv[0]), "r"(dv[1]),
+                                     "r"(dv[2]), "r"(dv[3])
+                                     : "memory");
                     const uint32_t fm0 = spread80(f0), fm1 = spread80(f1);
                     r[k] = (c[k] & fm0) | (r[k] & ~fm0);
                     r[k + 1] = (c[k + 1] & fm1) | (r[k + 1] & ~fm1);
@@ -515,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                                    n2 = __funnelshift_r(m[0], m[1], 16);
                     m[0] = n0; m[1] = n1; m[2] = n2;
                 }
-                if (nv < (uint32_t)kChunkBytes) { // bytes past the end of the frame are never entries (matters for T < 0)
+                if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) { // bytes past the end of the frame are never entries (matters for T < 0)
 #pragma unroll
                     for (int w = 0; w < kMaskWords; w++) {
                         const int vb = (int)nv - 32 * w;
@@ -523,12 +532,6 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     }
                 }
                 if (m[0] | m[1] | m[2]) {
-                    // park the difference bytes in this thread's own 96 bytes of the stage
-#pragma unroll
-                    for (int v = 0; v < kChunkWords / 4; v++)
-                        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(v)), "r"(dv[4 * v]),
-                                     "r"(dv[4 * v + 1]), "r"(dv[4 * v + 2]), "r"(dv[4 * v + 3])
-                                     : "memory");
                     if (REFREG) dirty = true;
                     else store_ref();
                 }
@@ -578,8 +581,9 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             const uint32_t base = sum_warps(red + (q & 1u) * kWarpsPad, lane);
             if (tid == 0) {
                 if (b == G - 1) {
-                    desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
-                    if (b_s == p.nseg - 1) p.pos[b_t] = base + b_total;
+                    if (!REFREG)
+                        desc_publish(p.desc + (size_t)(q - 1) * (G + 1) + G, ((unsigned long long)p.epoch << 32) | (base + b_total));
+                    if (REFREG || b_s == p.nseg - 1) p.pos[b_t] = base + b_total;
                 }
                 if ((size_t)base + b_total > p.cap) atomicOr(p.status, kStatusCapacity);
             }
@@ -636,7 +640,8 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
             b_wrank = incl - cnt; b_wexc = wexc; b_wtotal = wtotal; b_total = total;
             b_coff = coff; b_myaddr = myaddr; b_t = t; b_s = s;
             pending = true;
-            if (++s == p.nseg) { s = 0; ++t; }
+            if (REFREG) ++t;
+            else if (++s == p.nseg) { s = 0; ++t; }
             b_st = st;
             if (++st == nstages) st = 0;
         } else {
