@@ -168,12 +168,22 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 __device__ __forceinline__ void emit_bits(uint32_t bits, uint32_t jbase, uint32_t coff, uint32_t dvaddr, uint16_t *sxs,
                                           uint8_t *sd, uint32_t &o)
 {
+    // two entries per trip: half the loop overhead, and the two byte loads are in flight together.  With one bit
+    // left the second load reads the byte before the thread's chunk (harmless) and nothing is stored for it.
     while (bits) {
-        const uint32_t j = jbase + (uint32_t)__ffs((int)bits) - 1u;
+        const uint32_t j0 = jbase + (uint32_t)__ffs((int)bits) - 1u;
         bits &= bits - 1u;
-        sxs[o] = (uint16_t)(coff + j);
-        sd[o] = (uint8_t)lds_u8(dvaddr + j);
-        o++;
+        const bool two = bits != 0u;
+        const uint32_t j1 = jbase + (uint32_t)__ffs((int)bits) - 1u;
+        bits &= bits - 1u;
+        const uint32_t v0 = lds_u8(dvaddr + j0), v1 = lds_u8(dvaddr + j1);
+        sxs[o] = (uint16_t)(coff + j0);
+        sd[o] = (uint8_t)v0;
+        if (two) {
+            sxs[o + 1] = (uint16_t)(coff + j1);
+            sd[o + 1] = (uint8_t)v1;
+        }
+        o += two ? 2u : 1u;
     }
 }
 
