@@ -439,32 +439,44 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                 phase ^= 1u << st;
             }
             myaddr = stage_addr + st * kStageBytes + tid * kChunkBytes;
-            // Without a display filter the pixels are consumed 16 bytes at a time straight from the ring (one vector
-            // of look-ahead): 4 instead of 24 live registers.  The filters need whole pixel groups first.
+            // The pixels are consumed straight from the ring, a few registers at a time: 16 bytes (one vector of
+            // look-ahead) without a display filter, one 48-byte pixel group when a filter needs whole pixels.
             constexpr bool kStreamLoad = (MODE == kModeNone);
-            uint32_t c[kStreamLoad ? 1 : kChunkWords];
+            const bool pass_on = !(p.debug & 4u); // debug 4: skip the per-word pass (ingest-only experiment)
             // the chunk that holds the end of the frame: bytes past N never differ (slot word k of the chunk)
             auto clip_word = [&](int k, uint32_t cw) -> uint32_t {
                 const int vb = (int)nv - (int)(voff(k >> 2) + 4 * (k & 3)); // valid bytes from this slot word on
                 const uint32_t vm = vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << (8 * vb)) - 1u));
                 return (cw & vm) | (r[k] & ~vm);
             };
-            if (!kStreamLoad) {
-                if (nv) {
+            // ---- 3. (defined first, used per vector) one pass: flags -> 96-bit change mask, difference bytes,
+            //         negative feedback: reference := changed ? current : reference        (test.cu:565-570)
+            // four words (one 16-byte vector) of the chunk
+            auto pass_vector = [&](int v, const uint32_t (&cv)[4]) {
+                uint32_t dv[4];
 #pragma unroll
-                    for (int v = 0; v < kChunkWords / 4; v++) {
-                        uint4 x = lds128(myaddr + voff(v));
-                        c[4 * v] = x.x; c[4 * v + 1] = x.y; c[4 * v + 2] = x.z; c[4 * v + 3] = x.w;
-                    }
-                    if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
-#pragma unroll
-                        for (int k = 0; k < kChunkWords; k++) c[k] = clip_word(k, c[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < kChunkWords; k++) c[k] = r[k];
+                for (int h = 0; h < 4; h += 2) {
+                    const int k = 4 * v + h;
+                    const uint32_t f0 = changed80<HI>(absdiff4(cv[h], r[k]), p.addc);
+                    const uint32_t f1 = changed80<HI>(absdiff4(cv[h + 1], r[k + 1]), p.addc);
+                    // the eight flag bits of two words (7,15,23,31 and, shifted, 3,11,19,27) -> one byte of the change
+                    // mask: every partial product of the multiply lands on its own bit, and bits 32..39 of the product
+                    // are the flags in byte order
+                    const uint32_t g8 = __umulhi(f1 + (f0 >> 4), 0x20408100u);
+                    m[k >> 3] = __byte_perm(m[k >> 3], g8, ((k >> 1) & 3) == 0 ? 0x3214 : ((k >> 1) & 3) == 1 ? 0x3240
+                                                          : ((k >> 1) & 3) == 2 ? 0x3410 : 0x4210);
+                    dv[h] = sub4<true>(cv[h], r[k]);
+                    dv[h + 1] = sub4<true>(cv[h + 1], r[k + 1]);
+                    const uint32_t fm0 = spread80(f0), fm1 = spread80(f1);
+                    r[k] = (cv[h] & fm0) | (r[k] & ~fm0);
+                    r[k + 1] = (cv[h + 1] & fm1) | (r[k + 1] & ~fm1);
                 }
-            }
+                // park the difference bytes of this vector in the thread's own 96 bytes of the stage right away (needed
+                // only if the chunk has entries, but 24 live registers cost more than six unconditional shared stores)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(v)), "r"(dv[0]), "r"(dv[1]), "r"(dv[2]),
+                             "r"(dv[3])
+                             : "memory");
+            };
 
             // ---- 2. display filter on the same registers (reference as it was BEFORE this frame)
             if (MODE != kModeNone && nv) {
@@ -476,7 +488,16 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                     if (gnv == 0) continue;
                     uint32_t cg[kGroupWords], rg[kGroupWords], o[kGroupWords];
 #pragma unroll
-                    for (int k = 0; k < kGroupWords; k++) { cg[k] = c[g * kGroupWords + k]; rg[k] = r[g * kGroupWords + k]; }
+                    for (int v = 0; v < kGroupWords / 4; v++) {
+                        const uint4 x = lds128(myaddr + voff(g * (kGroupWords / 4) + v));
+                        cg[4 * v] = x.x; cg[4 * v + 1] = x.y; cg[4 * v + 2] = x.z; cg[4 * v + 3] = x.w;
+                    }
+                    if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
+#pragma unroll
+                        for (int k = 0; k < kGroupWords; k++) cg[k] = clip_word(g * kGroupWords + k, cg[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kGroupWords; k++) rg[k] = r[g * kGroupWords + k];
                     if (MODE == kModeHeat) {
                         uint32_t ad[kGroupWords];
 #pragma unroll
@@ -507,56 +528,28 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
                             }
                         }
                     }
+                    // the filter saw the reference as it was BEFORE this frame; now the pass over the same registers
+                    if (pass_on) {
+#pragma unroll
+                        for (int v = 0; v < kGroupWords / 4; v++) {
+                            const uint32_t cv[4] = {cg[4 * v], cg[4 * v + 1], cg[4 * v + 2], cg[4 * v + 3]};
+                            pass_vector(g * (kGroupWords / 4) + v, cv);
+                        }
+                    }
                 }
             }
 
-            // ---- 3. one pass: flags -> 96-bit change mask, difference bytes, negative feedback
-            //         reference := changed ? current : reference                      (test.cu:565-570)
-            if (!(p.debug & 4u)) { // debug 4: skip the per-word pass (ingest-only experiment)
-                // four words (one 16-byte vector) of the chunk
-                auto pass_vector = [&](int v, const uint32_t (&cv)[4]) {
-                    uint32_t dv[4];
-#pragma unroll
-                    for (int h = 0; h < 4; h += 2) {
-                        const int k = 4 * v + h;
-                        const uint32_t f0 = changed80<HI>(absdiff4(cv[h], r[k]), p.addc);
-                        const uint32_t f1 = changed80<HI>(absdiff4(cv[h + 1], r[k + 1]), p.addc);
-                        // the eight flag bits of two words (7,15,23,31 and, shifted, 3,11,19,27) -> one byte of the change
-                        // mask: every partial product of the multiply lands on its own bit, and bits 32..39 of the product
-                        // are the flags in byte order
-                        const uint32_t g8 = __umulhi(f1 + (f0 >> 4), 0x20408100u);
-                        m[k >> 3] = __byte_perm(m[k >> 3], g8, ((k >> 1) & 3) == 0 ? 0x3214 : ((k >> 1) & 3) == 1 ? 0x3240
-                                                              : ((k >> 1) & 3) == 2 ? 0x3410 : 0x4210);
-                        dv[h] = sub4<true>(cv[h], r[k]);
-                        dv[h + 1] = sub4<true>(cv[h + 1], r[k + 1]);
-                        const uint32_t fm0 = spread80(f0), fm1 = spread80(f1);
-                        r[k] = (cv[h] & fm0) | (r[k] & ~fm0);
-                        r[k + 1] = (cv[h + 1] & fm1) | (r[k + 1] & ~fm1);
-                    }
-                    // park the difference bytes of this vector in the thread's own 96 bytes of the stage right away (needed
-                    // only if the chunk has entries, but 24 live registers cost more than six unconditional shared stores)
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(v)), "r"(dv[0]), "r"(dv[1]), "r"(dv[2]),
-                                 "r"(dv[3])
-                                 : "memory");
-                };
-                if (kStreamLoad) {
-                    if (nv) {
-                        uint4 nx = lds128(myaddr + voff(0));
-#pragma unroll
-                        for (int v = 0; v < kChunkWords / 4; v++) {
-                            uint32_t cv[4] = {nx.x, nx.y, nx.z, nx.w};
-                            if (v + 1 < kChunkWords / 4) nx = lds128(myaddr + voff(v + 1));
-                            if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
-#pragma unroll
-                                for (int h = 0; h < 4; h++) cv[h] = clip_word(4 * v + h, cv[h]);
-                            }
-                            pass_vector(v, cv);
-                        }
-                    }
-                } else {
+            if (pass_on) {
+                if (kStreamLoad && nv) {
+                    uint4 nx = lds128(myaddr + voff(0));
 #pragma unroll
                     for (int v = 0; v < kChunkWords / 4; v++) {
-                        const uint32_t cv[4] = {c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]};
+                        uint32_t cv[4] = {nx.x, nx.y, nx.z, nx.w};
+                        if (v + 1 < kChunkWords / 4) nx = lds128(myaddr + voff(v + 1));
+                        if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
+#pragma unroll
+                            for (int h = 0; h < 4; h++) cv[h] = clip_word(4 * v + h, cv[h]);
+                        }
                         pass_vector(v, cv);
                     }
                 }
