@@ -113,6 +113,26 @@ def test_k1_fixture_changed_bytes(oracle):
     assert np.array_equal(oracle.client_apply(a, xs, diff), ref)
 
 
+def test_k1_committed_fixture_copies(oracle):
+    # the same pair as committed fixtures (tests/golden/k1_f1.jpg, k1_f2.jpg: byte copies of the reference's files),
+    # so the K1 pin also holds where /root/reference does not exist
+    cv2 = pytest.importorskip("cv2")
+    import hashlib
+    with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
+        g = json.load(f)
+    a = cv2.imread(os.path.join(GOLDEN, "k1_f1.jpg"))
+    b = cv2.imread(os.path.join(GOLDEN, "k1_f2.jpg"))
+    sha = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
+    assert sha(a) == g["sha256_f1"] and sha(b) == g["sha256_f2"]
+    pos, xs, diff, ref, _ = oracle.diff_compact(b, a, 20)
+    assert pos == 369350 == oracle.count_difference(a, b, 20)
+    assert sha(xs) == g["sha256_xs"] and sha(diff) == g["sha256_diff"] and sha(ref) == g["sha256_new_reference"]
+    if os.path.exists(os.path.join(REF, "tests/noise_filter_benchmark/f1.jpg")):
+        for mine, theirs in (("k1_f1.jpg", "f1.jpg"), ("k1_f2.jpg", "f2.jpg")):
+            with open(os.path.join(GOLDEN, mine), "rb") as x, open(os.path.join(REF, "tests/noise_filter_benchmark", theirs), "rb") as y:
+                assert x.read() == y.read()
+
+
 def test_golden_k1_record():
     # the K1 facts as recorded by tests/golden/make_golden.py in the build container (travels to the GPU box)
     with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
