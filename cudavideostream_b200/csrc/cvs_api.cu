@@ -113,6 +113,8 @@ struct Slot {
     unsigned int *d_pos = nullptr;
     uint8_t *d_show = nullptr;
     unsigned int *h_pos = nullptr; // pinned
+    unsigned int *d_status = nullptr; // StatusBits of this ticket's launches (cleared at submit)
+    unsigned int *h_status = nullptr; // pinned copy, valid once ev_pos has fired
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_pos = nullptr,
                 ev_p0 = nullptr, ev_done = nullptr;
     bool busy = false;
@@ -250,17 +252,34 @@ cvs_status ensure_work(cvs_handle h, size_t frames)
 cvs_status ensure_bin(cvs_handle h, size_t frames)
 {
     if (h->bin_frames >= frames) return CVS_OK;
-    if (h->d_gray1) {
+    if (h->d_gray1 || h->d_hist || h->d_thr) {
         CU_TRY(cudaDeviceSynchronize());
-        CU_TRY(cudaFree(h->d_gray1));
-        CU_TRY(cudaFree(h->d_hist));
-        CU_TRY(cudaFree(h->d_thr));
+        // forget the pointers before anything below can fail: a later call (or cvs_destroy) must not free them again
+        uint8_t *g = h->d_gray1;
+        unsigned int *hi = h->d_hist;
+        int *th = h->d_thr;
         h->d_gray1 = nullptr;
+        h->d_hist = nullptr;
+        h->d_thr = nullptr;
         h->bin_frames = 0;
+        cudaFree(g);
+        cudaFree(hi);
+        cudaFree(th);
     }
-    CU_TRY(cudaMalloc(&h->d_gray1, frames * h->P16 + 64));
-    CU_TRY(cudaMalloc(&h->d_hist, frames * 256 * sizeof(unsigned int)));
-    CU_TRY(cudaMalloc(&h->d_thr, frames * sizeof(int)));
+    uint8_t *g = nullptr;
+    unsigned int *hi = nullptr;
+    int *th = nullptr;
+    if (cudaMalloc(&g, frames * h->P16 + 64) != cudaSuccess || cudaMalloc(&hi, frames * 256 * sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&th, frames * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(g);
+        cudaFree(hi);
+        cudaFree(th);
+        return fail(CVS_ERR_NOMEM, "binarisation scratch for %zu frames does not fit", frames);
+    }
+    h->d_gray1 = g;
+    h->d_hist = hi;
+    h->d_thr = th;
     h->bin_frames = frames;
     return CVS_OK;
 }
@@ -306,18 +325,21 @@ cvs_status launch_conv(const uint8_t *in, uint8_t *out, int width, int height, s
 }
 
 // One pass of the whole hot path over nframes device-resident frames (A11, kernels.cu:455-520).
+// Long sequences are walked in pieces of at most max_sequence frames; every piece runs the complete chain (noise
+// filter / overlay pre-pass, fused stream kernel, binarisation pass 2), so the scratch buffers are sized by the piece
+// and no launch dimension grows with the length of the sequence.
+//   frames_private: d_frames is a buffer of this library (a slot's upload buffer) that may be modified in place --
+//                   the text overlay is then blitted straight into it instead of into a copy.
 cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int nframes, unsigned int *d_pos, int *d_xs,
                       uint8_t *d_diff, size_t cap, uint8_t *d_show, size_t show_stride, const char *text,
-                      cudaStream_t st)
+                      cudaStream_t st, bool frames_private, unsigned int *d_status)
 {
     if (nframes <= 0) return CVS_OK;
-    const uint8_t *frames = d_frames;
-    size_t fstride = stride;
 
     // ---- text overlay glyph indices (kernels.cu:466-473); characters outside the atlas are skipped
     cvs::OverlayText txt;
     txt.n = 0;
-    if (text && text[0] && h->d_glyphs) {
+    if (text && text[0] && h->d_glyphs && h->glyph_h <= h->height) {
         int n = (int)strlen(text);
         if (n > (int)sizeof txt.idx) n = (int)sizeof txt.idx;
         for (int j = 0; j < n; j++) {
@@ -327,38 +349,18 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         txt.n = n;
     }
 
-    // ---- pre-pass: noise filter and overlay write a private copy of the frames
-    if (h->noise_filter || txt.n) {
-        cvs_status s = ensure_work(h, (size_t)nframes);
-        if (s) return s;
-        if (h->noise_filter) {
-            s = launch_conv(d_frames, h->d_work, h->width, h->height, stride, h->Npad, nframes, h->ksize, h->weights, st);
-            if (s) return s;
-            h->launches++;
-        } else {
-            CU_TRY(cudaMemcpy2DAsync(h->d_work, h->Npad, d_frames, stride, h->N, nframes, cudaMemcpyDeviceToDevice, st));
-        }
-        if (txt.n && h->glyph_h <= h->height) {
-            const int area = 3 * h->glyph_w * h->glyph_h;
-            dim3 grid((area + 255) / 256, txt.n, nframes);
-            cvs::k_overlay<<<grid, 256, 0, st>>>(h->d_work, h->Npad, h->width, h->d_glyphs, h->glyph_w, h->glyph_h, txt);
-            CU_TRY(cudaGetLastError());
-            h->launches++;
-        }
-        frames = h->d_work;
-        fstride = h->Npad;
-    }
-
     const int mode = h->mode;
     const bool binarize = (mode == 5 || mode == 7) && d_show;
     const int kmode = d_show ? mode : 0; // without a display buffer only the payload is produced
-    if (binarize) {
-        cvs_status s = ensure_bin(h, (size_t)nframes);
+    const int piece_max = h->max_sequence < nframes ? h->max_sequence : nframes;
+    const bool need_work = h->noise_filter || (txt.n && !frames_private);
+    if (need_work) {
+        cvs_status s = ensure_work(h, (size_t)piece_max);
         if (s) return s;
-        CU_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)nframes * 256 * sizeof(unsigned int), st));
     }
-    if (kmode == 2) {
-        // nothing: the fused kernel writes every byte of the red-black frame
+    if (binarize) {
+        cvs_status s = ensure_bin(h, (size_t)piece_max);
+        if (s) return s;
     }
 
     // ---- geometry of the persistent launch
@@ -369,9 +371,11 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
     StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
-    // ring depth: see nstages in k_stream (CVS_STAGES overrides it for experiments)
+    // ring depth: see nstages in k_stream
     int nstages = refreg ? cvs::kStages : cvs::kStages - 1;
+#ifdef CVS_PROFILING
     if (h->stages >= 2 && h->stages <= cvs::kStages) nstages = h->stages;
+#endif
     const int smem_bytes = cvs::SmemLayout::total(nstages);
     int &occ = h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
     if (occ == 0) { // first launch of this variant on this handle
@@ -388,9 +392,35 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 
     int done = 0;
     while (done < nframes) {
-        int chunk = nframes - done;
-        if (chunk > h->max_sequence) chunk = h->max_sequence;
-        cvs_status s = ensure_desc(h, (size_t)chunk * nseg * (G + 1));
+        int piece = nframes - done;
+        if (piece > h->max_sequence) piece = h->max_sequence;
+        const uint8_t *frames = d_frames + (size_t)done * stride;
+        size_t fstride = stride;
+
+        // ---- pre-pass: the noise filter writes a private copy of the frames; the overlay is blitted into that
+        //      copy, into a plain copy, or (frames_private) into the frames themselves
+        if (h->noise_filter) {
+            cvs_status s = launch_conv(frames, h->d_work, h->width, h->height, stride, h->Npad, piece, h->ksize, h->weights, st);
+            if (s) return s;
+            h->launches++;
+            frames = h->d_work;
+            fstride = h->Npad;
+        } else if (txt.n && !frames_private) {
+            CU_TRY(cudaMemcpy2DAsync(h->d_work, h->Npad, frames, stride, h->N, piece, cudaMemcpyDeviceToDevice, st));
+            frames = h->d_work;
+            fstride = h->Npad;
+        }
+        if (txt.n) {
+            const int area = 3 * h->glyph_w * h->glyph_h;
+            dim3 grid((area + 255) / 256, txt.n, piece);
+            cvs::k_overlay<<<grid, 256, 0, st>>>(const_cast<uint8_t *>(frames), fstride, h->width, h->d_glyphs, h->glyph_w,
+                                                 h->glyph_h, txt);
+            CU_TRY(cudaGetLastError());
+            h->launches++;
+        }
+        if (binarize) CU_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)piece * 256 * sizeof(unsigned int), st));
+
+        cvs_status s = ensure_desc(h, (size_t)piece * nseg * (G + 1));
         if (s) return s;
         h->epoch++;
         if (h->epoch == 0) { // tag wrapped: stale descriptors could alias
@@ -398,9 +428,9 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
             h->epoch = 1;
         }
         cvs::StreamParams p;
-        p.frames = frames + (size_t)done * fstride;
+        p.frames = frames;
         p.frame_stride = fstride;
-        p.nframes = chunk;
+        p.nframes = piece;
         p.ref = h->d_ref;
         p.nbytes = h->N;
         p.nbytes16 = h->N16;
@@ -414,29 +444,30 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.cap = cap;
         p.show = d_show ? d_show + (size_t)done * show_stride : nullptr;
         p.show_stride = show_stride;
-        p.gray1 = binarize ? h->d_gray1 + (size_t)done * h->P16 : nullptr;
+        p.gray1 = binarize ? h->d_gray1 : nullptr;
         p.gray_stride = h->P16;
-        p.hist = binarize ? h->d_hist + (size_t)done * 256 : nullptr;
+        p.hist = binarize ? h->d_hist : nullptr;
         p.heat_lut = h->d_lut;
         p.desc = h->d_desc;
         p.epoch = h->epoch;
         p.addc = h->addc;
         p.debug = h->debug;
-        p.status = h->d_status;
+        p.status = d_status;
         void *args[] = {&p};
         CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(cvs::kThreads), args,
                                            (size_t)smem_bytes, st));
         h->launches++;
-        done += chunk;
-    }
 
-    if (binarize) {
-        cvs::k_threshold<<<nframes, 256, 0, st>>>(h->d_hist, h->d_thr, nframes, 50, 200);
-        CU_TRY(cudaGetLastError());
-        dim3 grid(grid_for((h->npix + 15) / 16, 256, h->sms), nframes);
-        cvs::k_binarize_expand<<<grid, 256, 0, st>>>(h->d_gray1, h->P16, d_show, show_stride, h->d_thr, h->npix);
-        CU_TRY(cudaGetLastError());
-        h->launches += 2;
+        if (binarize) {
+            cvs::k_threshold<<<piece, 256, 0, st>>>(h->d_hist, h->d_thr, piece, 50, 200);
+            CU_TRY(cudaGetLastError());
+            dim3 grid(grid_for((h->npix + 15) / 16, 256, h->sms), piece);
+            cvs::k_binarize_expand<<<grid, 256, 0, st>>>(h->d_gray1, h->P16, d_show + (size_t)done * show_stride, show_stride,
+                                                         h->d_thr, h->npix);
+            CU_TRY(cudaGetLastError());
+            h->launches += 2;
+        }
+        done += piece;
     }
     return CVS_OK;
 }
@@ -449,9 +480,8 @@ cvs_status check_handle(cvs_handle h)
     return CVS_OK;
 }
 
-cvs_status status_word(cvs_handle h)
+cvs_status status_word(unsigned int w)
 {
-    unsigned int w = *h->h_status;
     if (w & cvs::kStatusWatchdog) return fail(CVS_ERR_INTERNAL, "device watchdog tripped (status 0x%x)", w);
     if (w & cvs::kStatusCapacity) return fail(CVS_ERR_CAPACITY, "payload capacity exceeded");
     return CVS_OK;
@@ -530,8 +560,12 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     h->Npad = (size_t)h->nchunks * cvs::kChunkBytes;
     h->P16 = round_up(h->npix, 16);
     threshold_consts(cfg->threshold, h->hi, h->addc);
+#ifdef CVS_PROFILING
+    // timing experiments only (results are wrong by construction): compiled into profiling builds, never into the
+    // library a server links -- a stray environment variable must not be able to corrupt a stream
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
     if (const char *sg = getenv("CVS_STAGES")) h->stages = atoi(sg);
+#endif
     if (const char *pp = getenv("CVS_PAYLOAD_PUSH")) h->push_payload = atoi(pp) != 0;
     if (const char *sp = getenv("CVS_EGRESS_SPECULATE")) h->speculate = atoi(sp) != 0;
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
@@ -589,6 +623,10 @@ cvs_status init_device_state(cvs_handle h, const cvs_config *cfg)
         CU_TRY(cudaMalloc(&s.d_pos, sizeof(unsigned int)));
         if (h->mode) CU_TRY(cudaMalloc(&s.d_show, h->Npad + 64));
         CU_TRY(cudaHostAlloc(&s.h_pos, sizeof(unsigned int), cudaHostAllocDefault));
+        CU_TRY(cudaMalloc(&s.d_status, sizeof(unsigned int)));
+        CU_TRY(cudaMemset(s.d_status, 0, sizeof(unsigned int)));
+        CU_TRY(cudaHostAlloc(&s.h_status, sizeof(unsigned int), cudaHostAllocDefault));
+        *s.h_status = 0;
         cudaEvent_t *evs[] = {&s.ev_h2d0, &s.ev_h2d1, &s.ev_k0, &s.ev_k1, &s.ev_pos, &s.ev_p0, &s.ev_done};
         for (cudaEvent_t *e : evs) CU_TRY(cudaEventCreate(e));
     }
@@ -610,6 +648,8 @@ cvs_status cvs_destroy(cvs_handle h)
     for (Slot &s : h->slot) {
         cudaFree(s.d_in); cudaFree(s.d_xs); cudaFree(s.d_diff); cudaFree(s.d_pos); cudaFree(s.d_show);
         cudaFreeHost(s.h_pos);
+        cudaFree(s.d_status);
+        cudaFreeHost(s.h_status);
         cudaEvent_t evs[] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.ev_p0, s.ev_done};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
@@ -672,7 +712,9 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     const size_t cap = round_up(h->N, 4);
     uint8_t *dshow = (h->mode && show) ? s.d_show : nullptr;
     const double th1 = h->trace ? host_us() : 0;
-    st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp);
+    CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), h->s_comp));
+    st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp,
+                    /*frames_private=*/true, s.d_status);
     if (st) return st;
     const double th2 = h->trace ? host_us() : 0;
     CU_TRY(cudaEventRecord(s.ev_k1, h->s_comp));
@@ -695,10 +737,10 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     s.spec = 0;
     s.pushed = false;
     const uint32_t spec_lo = h->N / 64u < 262144u ? h->N / 64u : 262144u; // ~1.3 MB of payload at 1080p
-    if (h->speculate && diff_out != frame && h->pred >= spec_lo && h->pred <= h->N / 4u) {
-        size_t guess = h->pred ? h->pred : (size_t)h->N / 16;
-        guess = round_up(guess < 4096 ? 4096 : guess, 4);
-        s.spec = (uint32_t)(guess > cap ? cap : guess);
+    // only with a prediction from a previous frame, and never more entries than the caller's buffers hold (N)
+    if (h->speculate && diff_out != frame && h->pred != 0 && h->pred >= spec_lo && h->pred <= h->N / 4u) {
+        const size_t guess = round_up(h->pred, 4);
+        s.spec = (uint32_t)(guess > h->N ? h->N : guess);
     } else {
         s.pushed = h->push_payload && mapped_device_pointer(diff_out, &dev_diff) && mapped_device_pointer(xs, &dev_xs) &&
                    ((uintptr_t)dev_diff % 16 == 0) && ((uintptr_t)dev_xs % 16 == 0);
@@ -709,7 +751,7 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
         h->launches++;
     }
     CU_TRY(cudaMemcpyAsync(s.h_pos, s.d_pos, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
-    CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
+    CU_TRY(cudaMemcpyAsync(s.h_status, s.d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->s_d2h));
     if (s.spec) {
         CU_TRY(cudaMemcpyAsync(diff_out, s.d_diff, s.spec, cudaMemcpyDeviceToHost, h->s_d2h));
         CU_TRY(cudaMemcpyAsync(xs, s.d_xs, (size_t)s.spec * sizeof(int), cudaMemcpyDeviceToHost, h->s_d2h));
@@ -739,10 +781,12 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
     if (st) return st;
     Slot &s = h->slot[ticket % kSlots];
     if (!s.busy || s.ticket != ticket) return fail(CVS_ERR_INVALID, "unknown ticket %llu", (unsigned long long)ticket);
-    s.busy = false;
     CU_TRY(cudaEventSynchronize(s.ev_pos));
-    st = status_word(h);
-    if (st == CVS_ERR_INTERNAL) return st;
+    st = status_word(*s.h_status);
+    if (st == CVS_ERR_INTERNAL) {
+        s.busy = false; // the ticket is consumed: its launch gave up, there is nothing to deliver
+        return st;
+    }
     const unsigned int n = *s.h_pos;
     // payload (kernels.cu:522-523): diff bytes over the head of the frame buffer, then the indices
     // (on their own stream: s_d2h already holds the work of the younger tickets, and anything queued behind
@@ -755,6 +799,7 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
         CU_TRY(cudaEventRecord(s.ev_done, h->s_pay));
         CU_TRY(cudaEventSynchronize(s.ev_done));
     }
+    s.busy = false; // from here on nothing can fail: the slot may be reused
     *s.u_pos = n;
     h->pred = n + (n / 16 > 16384 ? n / 16 : 16384); // change density is strongly correlated from frame to frame
     h->last_slot = (int)(ticket % kSlots);
@@ -781,14 +826,22 @@ cvs_status cvs_get_timing(cvs_handle h, float *h2d_us, float *kernel_us, float *
     if (!h) return fail(CVS_ERR_INVALID, "null handle");
     if (h->last_slot >= 0) { // the events of the last completed ticket are read on demand, not per frame
         Slot &s = h->slot[h->last_slot];
+        // the slot's events may already have been re-recorded by a younger ticket that is still in flight
+        // (cudaErrorNotReady): keep the previous values then
         float a = 0, b = 0, c = 0, d = 0;
-        CU_TRY(cudaEventElapsedTime(&a, s.ev_h2d0, s.ev_h2d1));
-        CU_TRY(cudaEventElapsedTime(&b, s.ev_k0, s.ev_k1));
-        CU_TRY(cudaEventElapsedTime(&c, s.ev_p0, s.ev_pos));
-        if (s.copied) CU_TRY(cudaEventElapsedTime(&d, s.ev_pos, s.ev_done));
-        h->t_h2d = a * 1000.f;
-        h->t_kernel = b * 1000.f;
-        h->t_d2h = (c + d) * 1000.f;
+        cudaError_t e = cudaEventElapsedTime(&a, s.ev_h2d0, s.ev_h2d1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, s.ev_k0, s.ev_k1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&c, s.ev_p0, s.ev_pos);
+        if (e == cudaSuccess && s.copied) e = cudaEventElapsedTime(&d, s.ev_pos, s.ev_done);
+        if (e == cudaSuccess) {
+            h->t_h2d = a * 1000.f;
+            h->t_kernel = b * 1000.f;
+            h->t_d2h = (c + d) * 1000.f;
+        } else if (e == cudaErrorNotReady) {
+            cudaGetLastError();
+        } else {
+            return fail(CVS_ERR_CUDA, "cudaEventElapsedTime failed: %s", cudaGetErrorString(e));
+        }
     }
     if (h2d_us) *h2d_us = h->t_h2d;
     if (kernel_us) *kernel_us = h->t_kernel;
@@ -829,7 +882,8 @@ cvs_status cvs_run_sequence_device(cvs_handle h, const uint8_t *d_frames, size_t
         return fail(CVS_ERR_INVALID, "payload_capacity must be a positive multiple of 4");
     h->seq_status = CVS_OK;
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    st = run_frames(h, d_frames, frame_stride, nframes, d_pos, d_xs, d_diff, payload_capacity, d_show, show_stride, text, s);
+    st = run_frames(h, d_frames, frame_stride, nframes, d_pos, d_xs, d_diff, payload_capacity, d_show, show_stride, text, s,
+                    /*frames_private=*/false, h->d_status);
     if (st) return st;
     CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
     return CVS_OK;
@@ -839,7 +893,7 @@ cvs_status cvs_sequence_status(cvs_handle h)
 {
     cvs_status st = check_handle(h);
     if (st) return st;
-    st = status_word(h);
+    st = status_word(*h->h_status);
     if (*h->h_status) { // sticky bits are cleared once reported
         CU_TRY(cudaMemset(h->d_status, 0, sizeof(unsigned int)));
         *h->h_status = 0;

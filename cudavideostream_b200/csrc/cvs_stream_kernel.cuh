@@ -69,7 +69,7 @@ constexpr int kGroupsPerThread = 2;
 constexpr int kChunkBytes = kGroupsPerThread * kGroupBytes;   // 96
 constexpr int kChunkWords = kChunkBytes / 4;                  // 24
 constexpr int kMaskWords = kChunkBytes / 32;                  // 3
-constexpr int kStageBytes = kThreads * kChunkBytes;   // 24,576 B: one block slice
+constexpr int kStageBytes = kThreads * kChunkBytes;   // 49,152 B: one block slice
 constexpr int kStages = 4;                            // one parked, one in process, two slices in flight
 constexpr int kWarpEntries = 512;                     // payload entries a warp's staging window holds
 constexpr uint32_t kWatchdogPolls = 1u << 24;         // look-back polls (>= 100 ns each) before giving up

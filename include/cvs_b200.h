@@ -5,7 +5,7 @@
  * The reference exposes this path as the C++ class diff::cuda::CUDACore
  * (server/include/kernels.cuh:13-43; implementation server/src/kernels.cu:377-536).  Its four
  * public members are re-implemented, with unchanged signatures, by include/cvs_cuda_core.hpp +
- * cudavideostream_b200/csrc/cvs_shim.cpp, which are thin calls into the functions declared here.
+ * cudavideostream_b200/csrc/cvs_shim.cu, which are thin calls into the functions declared here.
  * Every entry point below names the reference interface it replaces.  Plain pointers and sizes
  * only; no CUDA, torch or OpenCV types appear in any signature (a cudaStream_t is passed as void*).
  *
@@ -15,6 +15,21 @@
  *
  * Pixel layout everywhere: packed row-major BGR24 ("RGB24" in OpenCV byte order), no row padding,
  * N = 3*width*height bytes per frame.
+ *
+ * Which of the reference's two implementations is the contract: the CPU loops.  Where
+ * the reference's CUDA kernels compute something else, this library follows the CPU loop, and a server that switches
+ * from kernels.cu to this library sees the CPU result:
+ *   - weighted gray (modes 4, 5): double products, left-to-right double adds, truncation
+ *     (tests/grayscale-weighted/cpu.cu:38-42); kernels.cu:67-95 accumulates the same products in a float;
+ *   - binarisation threshold (modes 5, 7): the CPU "two max" loop with its quirk (server.cpp:108-127: the previous
+ *     running arg-max, clamp [50,200]); kernels.cu:176-206 compute_max takes the arg-max of the even and of the odd bins;
+ *   - noise filter: float accumulator -> (uint8_t) as x86-64 converts it (cvttss2si, low byte: out-of-range values
+ *     wrap); CUDA's float-to-u8 conversion in kernels.cu:134 saturates.  With the reference's non-negative,
+ *     normalised weights the accumulator never leaves [0, 255] and both agree.
+ *
+ * Threading: a cvs_handle is NOT thread-safe -- one host thread at a time may call into a given handle (the reference
+ * calls exec_core from its main thread only, server.cpp:139).  Different handles may be used from different threads
+ * concurrently.  Tickets of one handle complete in submission order and must be waited for in that order.
  */
 #ifndef CVS_B200_H_
 #define CVS_B200_H_

@@ -242,3 +242,70 @@ def test_golden_real_camera_crop(cvs):
     assert np.array_equal(xs, g["xs"]) and np.array_equal(diff, g["diff"])
     assert np.array_equal(s.reference(), g["new_reference"])
     s.close()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (5, 1), (3, 3)])
+def test_submit_io_tiny_frames_stay_inside_the_buffers(cvs, oracle, w, h):
+    # N not a multiple of 4: neither the push nor a speculative copy may touch anything past N bytes / N ints of
+    # the caller's buffers (guard words behind them must survive), first frame and later frames alike
+    n = 3 * w * h
+    rng = np.random.default_rng(n)
+    base = rng.integers(0, 256, n, dtype=np.uint8)
+    s = cvs.Stream(w, h, base)
+    oc = oracle.OracleCore(w, h, base)
+    fin = cvs.alloc_host(n + 64)
+    dout = cvs.alloc_host(n + 64)
+    xout = cvs.alloc_host(4 * n + 64)
+    pb = (C.c_uint * 1)()
+    for t in range(6):
+        f = rng.integers(0, 256, n, dtype=np.uint8)
+        fin.array()[:n] = f
+        dout.array()[:] = 0xA5
+        xout.array()[:] = 0xA5
+        tk = s.submit_io_raw(fin.ptr, dout.ptr, None, "", C.addressof(pb), xout.ptr)
+        s.wait(tk)
+        opos, oxs, odiff, _, _ = oc.exec_core(f)
+        assert pb[0] == opos
+        assert np.array_equal(dout.array()[:opos], odiff) and np.array_equal(xout.array(np.int32)[:opos], oxs)
+        assert bool((dout.array()[n:] == 0xA5).all()), f"frame {t}: write past diff_out[N]"
+        assert bool((xout.array()[4 * n:] == 0xA5).all()), f"frame {t}: write past xs[N]"
+        assert np.array_equal(fin.array()[:n], f)
+    assert np.array_equal(s.reference(), oc.reference())
+    s.close()
+
+
+def test_long_sequence_is_walked_in_pieces(cvs, oracle):
+    # nframes > max_sequence: the whole chain (noise filter + overlay pre-pass, stream kernel, binarisation pass 2)
+    # runs piece by piece on scratch sized by the piece
+    import torch
+    w, h, T = 64, 48, 11
+    n = 3 * w * h
+    stride = (n + 15) // 16 * 16
+    k = oracle.gaussian_kernel(3, 1.5)
+    atlas = glyph_atlas(7, 5)
+    base, frames = random_sequence(w, h, T, 0.1, seed=4)
+    d_frames = torch.zeros(T * stride + 64, dtype=torch.uint8, device="cuda")
+    for t in range(T):
+        d_frames[t * stride:t * stride + n] = torch.from_numpy(frames[t]).cuda()
+    cap = (n + 3) // 4 * 4
+    d_pos = torch.zeros(T, dtype=torch.int32, device="cuda")
+    d_xs = torch.empty(T * cap, dtype=torch.int32, device="cuda")
+    d_diff = torch.empty(T * cap, dtype=torch.uint8, device="cuda")
+    d_show = torch.zeros(T * stride, dtype=torch.uint8, device="cuda")
+    s = cvs.Stream(w, h, base, mode=5, noise_filter=True, ksize=3, kweights=k, glyphs=atlas, glyph_w=7, glyph_h=5,
+                   max_sequence=4)
+    s.run_sequence_device(d_frames.data_ptr(), stride, T, d_pos.data_ptr(), d_xs.data_ptr(), d_diff.data_ptr(), cap,
+                          d_show.data_ptr(), stride, text="FPS 12", cuda_stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    s.sequence_status()
+    oc = oracle.OracleCore(w, h, base, mode=5, noise_filter=1, K=3, k=k, glyphs=atlas, gw=7, gh=5, chars=CHARS_STR)
+    for t in range(T):
+        opos, oxs, odiff, oshow, _ = oc.exec_core(frames[t], "FPS 12")
+        assert int(d_pos[t]) == opos, f"frame {t}"
+        assert np.array_equal(d_xs[t * cap:t * cap + opos].cpu().numpy(), oxs), f"frame {t}"
+        assert np.array_equal(d_diff[t * cap:t * cap + opos].cpu().numpy(), odiff), f"frame {t}"
+        assert np.array_equal(d_show[t * stride:t * stride + n].cpu().numpy(), oshow), f"frame {t}: show"
+        # the caller's frames are never modified (the overlay goes into a private copy)
+        assert np.array_equal(d_frames[t * stride:t * stride + n].cpu().numpy(), frames[t])
+    assert np.array_equal(s.reference(), oc.reference())
+    s.close()
