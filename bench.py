@@ -4,13 +4,21 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through libcvs_b200.so)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
 
-Workload (BASELINE.json configs[1]): 1080p BGR24 synthetic 300-frame sequences at change densities
+Headline workload (BASELINE.json configs[1]): 1080p BGR24 synthetic 300-frame sequences at change densities
 1 % / 10 % / 50 %, thresholded diff + negative feedback + ordered compaction.  One STEP = one pass over the
 three 300-frame sequences (900 frames, 5.6 GB of frames resident in HBM, so every frame is L2-cold).
 `value` = frames/s with the frames already in HBM (device-resident sequence API); `e2e` = frames/s through the
-pipelined drop-in call (cvs_submit/cvs_wait) with frames in pinned HOST memory, H2D and payload D2H inside
-the timed region.  Multi-GPU: one process per GPU, independent camera streams per rank, no collective on the
-data path (weak scaling); torch.distributed is used only for the barrier and the max-over-ranks time.
+pipelined drop-in call (cvs_submit_io/cvs_wait) with frames in pinned HOST memory, H2D and payload D2H inside
+the timed region (the three camera streams of a GPU are interleaved, so both PCIe directions stay busy), with the
+synchronous drop-in call (cvs_exec, what the unchanged server.cpp:139 does) next to it.
+
+Side workloads, each event-timed with its own algorithmic-byte roofline (config.workloads[]):
+  config3   1080p, Gaussian K=3 noise filter -> diff, weighted gray -> histogram -> two-max -> binarize   (3 2/3 + 6c) N
+  config4   1080p, diff + heat map (mode 1) and diff + heat-map-red (mode 2)                             (3 + 6c) N
+  config5   eight independent 3840x2160 streams, diff + compact, stream s on rank s mod N                (2 + 6c) N
+
+Multi-GPU: one process per GPU, independent camera streams per rank, no collective on the data path (weak
+scaling); torch.distributed is used only for the barrier and the max-over-ranks time.
 """
 from __future__ import annotations
 
@@ -33,11 +41,26 @@ DENSITIES_PPM = (10000, 100000, 500000)
 SEQ_FRAMES = 300
 METRIC = "1080p frames/sec (diff+compact, 300-frame sequences at 1%/10%/50% change density)"
 THR = 20
+BASE_SEED = 0xC0DA5EED
+W4K, H4K = 3840, 2160
+N4K = 3 * W4K * H4K
+C5_STREAMS, C5_FRAMES, C5_DENSITY = 8, 48, 100000
 
 
-def algorithmic_bytes(nframes: int, sum_pos: int) -> int:
-    """(2 + 6c) N + 4 per frame = read cur N + read ref N + write ref cN + payload 5cN + count."""
-    return nframes * (2 * N + 4) + 6 * sum_pos
+def workload_config(frames: int) -> dict:
+    """The workload both arms run -- identical in `--impl ours` and `--impl reference` lines."""
+    name = "1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H)
+    return {"workload": "%s_seq%d_d1_10_50" % (name, frames), "width": W, "height": H, "threshold": THR,
+            "frames_per_sequence": frames, "sequences_per_step": len(DENSITIES_PPM), "densities_ppm": list(DENSITIES_PPM),
+            "seed": "0x%X" % BASE_SEED, "streams_per_gpu": len(DENSITIES_PPM),
+            "l2": "inputs larger than L2: 3 x %.2f GB device-resident frame sequences per step" % (frames * N / 1e9)}
+
+
+def algorithmic_bytes(nframes: int, sum_pos: int, n: int = None, per_frame_n: float = 2.0) -> int:
+    """(k + 6c) N + 4 per frame; k = 2 diff+compact (read cur N + read ref N, + write ref cN +
+    payload 5cN + count), 3 with one fused display frame, 3 2/3 for config 3."""
+    n = N if n is None else n
+    return int(nframes * (per_frame_n * n + 4) + 6 * sum_pos)
 
 
 def hbm_model_bytes(nframes: int, sum_pos: int) -> int:
@@ -90,29 +113,22 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's CPU loop (oracle restatement of tests/cuda_streaming/test.cu:560-576), one
-# independent camera stream per host thread.
+# independent camera stream per host thread, on the first frames of the very sequences the GPU arm is timed on.
 # ------------------------------------------------------------------------------------------------------
-def host_ring(nring: int, density_ppm: int, seed: int):
-    from cudavideostream_b200 import synth
-    base = synth.base_frame(W, H, seed)
-    ring = np.empty((nring, N), dtype=np.uint8)
-    prev = base
-    for t in range(nring):
-        prev = synth.next_frame(prev, seed, t, density_ppm)
-        ring[t] = prev
-    # walked back and forth, so that consecutive frames are always one synthetic step apart
-    ring = np.ascontiguousarray(np.concatenate([ring, ring[-2:0:-1]]))
-    return base, ring
-
-
+CPU_RING = 12  # frames of each density's sequence the CPU legs walk (forth and back)
 _RINGS = None
 
 
 def cpu_rings():
-    """Host frame rings of the three densities (generated once per process: the numpy camera is slow)."""
+    """(base, ring) per density: frames 1..CPU_RING of the bench sequences (seed 0xC0DA5EED, rank 0), generated by the
+    oracle's C twin of the synthetic camera, walked forth and back so consecutive frames stay one step apart."""
     global _RINGS
     if _RINGS is None:
-        _RINGS = [host_ring(4, d, 0xC0DA5EED) for d in DENSITIES_PPM]
+        from oracle import oracle as orc
+        _RINGS = []
+        for d in DENSITIES_PPM:
+            base, fr = orc.synth_sequence(W, H, CPU_RING, d, BASE_SEED)
+            _RINGS.append((base, np.ascontiguousarray(np.concatenate([fr, fr[-2:0:-1]]))))
     return _RINGS
 
 
@@ -121,20 +137,22 @@ def cpu_run(target_seconds: float, threads: int):
     from oracle import oracle as orc
     orc.build()
     rings = cpu_rings()
-    # calibrate: one frame per thread per density
-    t_cal = sum(orc.bench_diff_compact(r, b, THR, 1, threads)[0] for b, r in rings)
+    t_cal = sum(orc.bench_diff_compact(r, b, THR, 1, threads)[0] for b, r in rings)  # one frame per thread per density
     iters = max(1, int(target_seconds / max(t_cal, 1e-3)))
     iters = min(iters, 50)
     sec = 0.0
     frames = 0
+    sum_pos = 0
     for b, r in rings:
-        s, nf, _ = orc.bench_diff_compact(r, b, THR, iters, threads)
+        s, nf, sp = orc.bench_diff_compact(r, b, THR, iters, threads)
         sec += s
         frames += nf
+        sum_pos += sp
     return {"value": frames / sec, "seconds": sec, "frames": frames, "cores": threads, "kind": "port",
-            "unit": "frames/s",
-            "sample": f"{iters} frames x {threads} independent streams x 3 densities (1/10/50 %) of the 1080p "
-                      f"workload, oracle/cvs_oracle.c orc_diff_compact -O2, frames in host RAM"}
+            "unit": "frames/s", "realised_c": sum_pos / (frames * N),
+            "sample": f"{iters} frames x {threads} independent streams x 3 densities (1/10/50 %): the first {CPU_RING} "
+                      f"frames of the bench's own 1080p sequences (seed 0x{BASE_SEED:X}) walked forth and back, "
+                      f"oracle/cvs_oracle.c orc_diff_compact (test.cu:560-576) -O2, frames in host RAM"}
 
 
 def cpu_single_thread(frames_per_density: int = 4):
@@ -149,6 +167,33 @@ def cpu_single_thread(frames_per_density: int = 4):
             sec += orc.bench_diff_compact(r, b, THR, frames_per_density, 1, o0=o0)[0]
         out["frames_per_s_1thread_" + name] = 3 * frames_per_density / sec
     return out
+
+
+def reference_binaries(gpu: bool):
+    """The reference's OWN code where it could be compiled (oracle/_ref/, built from the unmodified sources by
+    oracle/build_ref.py): ms per 1080p frame between readCap() returning and writeShow() being called in the
+    unmodified server.cpp main loop.  cpu = its CPU filter chain (server.cpp:96-135: gray, histogram, two-max,
+    binarize -- NOT the diff, which is commented out there); refgpu = its own kernels.cu on this GPU (exec_core incl.
+    its synchronous H2D/D2H); dropin = the same server.cpp linked against libcvs_b200.so."""
+    try:
+        from oracle import oracle as orc, ref_server
+        base, fr = orc.synth_sequence(W, H, 10, 100000, BASE_SEED)
+        out = {}
+        names = ["ref_server_cpu", "ref_server_cpu_O0"] + (["ref_server_refgpu", "ref_server_dropin"] if gpu else [])
+        for name in names:
+            if ref_server.binary(name) is None:
+                continue
+            try:
+                _, times = ref_server.run(name, W, H, base, fr, want_times=True, timeout=120)
+                out[name + "_ms_per_frame"] = float(np.median(times[2:])) / 1e6
+            except Exception as e:  # the reference's kernels read/write past their buffers: a fault is theirs
+                out[name + "_error"] = str(e)[:200]
+        if out:
+            out["what"] = ("median ms per 1080p frame (10 % density) inside the reference's unmodified server.cpp loop, "
+                           "readCap() -> writeShow(); kind: reference")
+        return out or None
+    except Exception:
+        return None
 
 
 def reference_arm(args):
@@ -168,10 +213,11 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sec / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), args.frames),
-                       "width": W, "height": H, "threshold": THR},
+            "config": workload_config(args.frames),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": vals[0]["sample"], "single_thread": cpu_single_thread()},
+                             "sample": vals[0]["sample"], "realised_c": vals[0]["realised_c"],
+                             "single_thread": cpu_single_thread(),
+                             "reference_binaries": reference_binaries(gpu=False)},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.time() - t0}
     print(json.dumps(line), flush=True)
@@ -181,6 +227,22 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def gaussian_k3():
+    """computeGaussianKernel, server/src/server.cpp:20-36 (K = 3, sigma = K*K/6)."""
+    K = 3
+    sigma = np.float32(K * K / 6.0)
+    k = np.empty(K * K, dtype=np.float32)
+    total = np.float32(0)
+    for i in range(K):
+        for j in range(K):
+            x = np.float32(i - (K - 1) / 2.0)
+            y = np.float32(j - (K - 1) / 2.0)
+            v = (1.0 / (2.0 * np.pi * float(sigma) * float(sigma))) * np.exp(-((float(x) * float(x) + float(y) * float(y)) / (2.0 * float(sigma) * float(sigma))))
+            k[i * K + j] = np.float32(v)
+            total = np.float32(total + k[i * K + j])
+    return (k / total).astype(np.float32)
+
+
 def ours(args):
     import torch
     import torch.distributed as dist
@@ -192,37 +254,39 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # one host thread + one context per GPU, pinned buffers NUMA-local to it: bind this rank
-        # to the CPUs nearest its GPU before any pinned allocation is first touched
+        # one host thread + one context per GPU, pinned buffers NUMA-local to it
         try:
             import pynvml
             pynvml.nvmlInit()
             pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
         except Exception:
             pass
-    if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cvs.load_library()
     st = torch.cuda.current_stream().cuda_stream
     T = args.frames
-    seed = 0xC0DA5EED ^ (rank * 0x9E3779B9)
+    seed = BASE_SEED ^ (rank * 0x9E3779B9)
     cap = (N + 3) // 4 * 4  # worst case: every byte of a frame changes
 
-    # ---- device-resident sequences, one Stream (reference state) per density
+    def device_sequence(w, h, nframes, density, sd):
+        n = 3 * w * h
+        frames = torch.empty((nframes + 1) * n, dtype=torch.uint8, device=dev)
+        cvs.synth.base_frame_device(frames.data_ptr(), w, h, sd, st)
+        for t in range(nframes):
+            cvs.synth.next_frame_device(frames.data_ptr() + t * n, frames.data_ptr() + (t + 1) * n, w, h, sd, t, density, st)
+        return frames
+
+    # ---- headline: device-resident sequences, one Stream (reference state) per density
     seqs = []
     for d in DENSITIES_PPM:
-        frames = torch.empty((T + 1) * N, dtype=torch.uint8, device=dev)
-        cvs.synth.base_frame_device(frames.data_ptr(), W, H, seed, st)
-        for t in range(T):
-            cvs.synth.next_frame_device(frames.data_ptr() + t * N, frames.data_ptr() + (t + 1) * N, W, H, seed, t, d, st)
+        frames = device_sequence(W, H, T, d, seed)
         torch.cuda.synchronize()
         base = frames[:N].cpu().numpy()
-        c = cap
         s = cvs.Stream(W, H, base, threshold=THR, device=local, max_sequence=max(T, 16))
-        seqs.append({"d": d, "frames": frames, "stream": s, "cap": c,
+        seqs.append({"d": d, "frames": frames, "stream": s, "cap": cap,
                      "pos": torch.zeros(T, dtype=torch.int32, device=dev),
-                     "xs": torch.empty(T * c, dtype=torch.int32, device=dev),
-                     "diff": torch.empty(T * c, dtype=torch.uint8, device=dev)})
+                     "xs": torch.empty(T * cap, dtype=torch.int32, device=dev),
+                     "diff": torch.empty(T * cap, dtype=torch.uint8, device=dev)})
 
     def run_seq(q):
         q["stream"].run_sequence_device(q["frames"].data_ptr() + N, N, T, q["pos"].data_ptr(), q["xs"].data_ptr(),
@@ -246,7 +310,6 @@ def ours(args):
     sampler.start()
     evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in seqs]
            for _ in range(args.steps)]
-    sum_pos = [0 for _ in seqs]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -268,10 +331,11 @@ def ours(args):
     tot_ms = 0.0
     for i, q in enumerate(seqs):
         ms = [evs[k][i][0].elapsed_time(evs[k][i][1]) for k in range(args.steps)]
-        sp = int(q["pos"].to(torch.int64).sum().item())  # identical in every timed step? (ring restarts): last step
+        sp = int(q["pos"].to(torch.int64).sum().item())
         alg, hbm = algorithmic_bytes(T, sp), hbm_model_bytes(T, sp)
         mean_ms = float(np.mean(ms))
         per_density.append({"density_ppm": q["d"], "realised_c": sp / (T * N), "ms_per_launch": mean_ms,
+                            "us_per_frame": 1e3 * mean_ms / T,
                             "frames_per_s": T / (mean_ms * 1e-3), "algorithmic_GBps": alg / (mean_ms * 1e-3) / 1e9,
                             "hbm_model_GBps": hbm / (mean_ms * 1e-3) / 1e9})
         tot_alg += alg
@@ -284,9 +348,6 @@ def ours(args):
     elapsed_ms = elapsed_s * 1e3
     value = frames_total / elapsed_s
 
-    # ---- end to end through the drop-in call: frames in pinned host memory, pipelined submit/wait
-    e2e = e2e_run(cvs, torch, dist, args, seqs, local, world, barrier)
-
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -294,28 +355,41 @@ def ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- end to end through the drop-in call: frames in pinned host memory, pipelined submit/wait
+    e2e = e2e_run(cvs, torch, args, seqs, local, barrier)
+
+    # ---- side workloads (BASELINE.json configs 3, 4, 5), event-timed like the headline
+    workloads = [] if args.no_side else side_workloads(cvs, torch, args, seqs, dev, local, rank, world, st, peak, barrier,
+                                                       device_sequence)
+
     achieved = tot_alg / (tot_ms * 1e-3) / 1e9
     achieved_hbm = tot_hbm / (tot_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tj = json.load(fh)
             # ncu dram__bytes_read.sum + dram__bytes_write.sum per frame (mean of the three densities) x frames per launch
-            traffic = json.load(fh)["dram_bytes_per_frame_mean"] * T if (W, H) == (1920, 1080) else None
+            traffic = tj["dram_bytes_per_frame_mean"] * T if (W, H) == (1920, 1080) else None
+            traffic_src = "static: profiles/traffic.json (one ncu --set full capture, %s), not measured in this run" % tj.get("kernel", "k_stream")
     except Exception:
         pass
 
     if rank == 0:
+        cfg = workload_config(T)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        kname = os.environ.get("CVS_STREAM_KERNEL", "ws")
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "%s_seq%d_d1_10_50" % ("1080p" if (W, H) == (1920, 1080) else "%dx%d" % (W, H), T), "width": W, "height": H, "threshold": THR,
-                           "frames_per_sequence": T, "sequences_per_step": len(seqs), "streams_per_gpu": len(seqs),
-                           "l2": "inputs larger than L2: 3 x %.2f GB device-resident frame sequences per step" % (T * N / 1e9),
-                           "per_density": per_density},
+                "config": cfg, "per_density": per_density, "workloads": workloads,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic,
+                             "traffic_source": traffic_src,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)",
-                             "kernel": "cvs::k_stream<0,false,%s> (one launch = one %d-frame sequence)" % ("true" if (N + 95) // 96 <= 512 * torch.cuda.get_device_properties(dev).multi_processor_count else "false", T),
+                             "kernel": "cvs::%s<0,false,%s> (one launch = one %d-frame sequence)" % (
+                                 "k_stream" if kname == "v1" else "k_stream_ws",
+                                 "true" if (N + 95) // 96 <= 512 * sms else "false", T),
                              "achieved_hbm_model": achieved_hbm, "frac_hbm_model": achieved_hbm / peak,
                              "note": "achieved = SURVEY 8(d) algorithmic bytes (2+6c)N+4 per frame / event-timed launch; "
                                      "hbm_model counts only bytes that must cross HBM when the reference stays on chip "
@@ -323,8 +397,9 @@ def ours(args):
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches_total}
         if world == 1 and not args.no_cpu:
             cb = cpu_run(args.cpu_seconds, os.cpu_count() or 1)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "realised_c")}
             line["cpu_baseline"]["single_thread"] = cpu_single_thread()
+            line["cpu_baseline"]["reference_binaries"] = reference_binaries(gpu=True)
         print(json.dumps(line), flush=True)
     for q in seqs:
         q["stream"].close()
@@ -333,10 +408,104 @@ def ours(args):
     return 0
 
 
-def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
-    """frames/s through cvs_submit/cvs_wait with HOST frames: per frame an H2D of N bytes from pinned memory and a
+def side_workloads(cvs, torch, args, seqs, dev, local, rank, world, st, peak, barrier, device_sequence):
+    """BASELINE.json configs 3, 4 and 5 as extra event-timed entries (the headline `value` stays config 2)."""
+    T = args.frames
+    reps = max(1, min(args.steps, 3))
+    out = []
+    frames10 = seqs[1]["frames"]   # the 10 % sequence of the headline
+    base10 = frames10[:N].cpu().numpy()
+    cap = seqs[1]["cap"]
+    pos = torch.zeros(T, dtype=torch.int32, device=dev)
+    xs = seqs[0]["xs"]             # payload buffers are reused: the workloads run one after the other
+    df = seqs[0]["diff"]
+    show = torch.empty(T * N, dtype=torch.uint8, device=dev)
+
+    def timed(fn, n_rep):
+        fn()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(n_rep):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+        return float(np.mean(ms))
+
+    specs = [("config3_noiseK3_gray_weighted_binarize", dict(mode=5, noise_filter=True, ksize=3, kweights=gaussian_k3()), 11.0 / 3.0,
+              "(3 2/3 + 6c) N: diff+compact + gray byte written and read + binarised frame written"),
+             ("config4_heat_map", dict(mode=1), 3.0, "(3 + 6c) N: diff+compact + one display frame"),
+             ("config4_heat_map_red", dict(mode=2), 3.0, "(3 + 6c) N: diff+compact + one display frame")]
+    for name, kw, k_n, note in specs:
+        s = cvs.Stream(W, H, base10, threshold=THR, device=local, max_sequence=max(T, 16), **kw)
+        l0 = s.launch_count()
+
+        def run():
+            s.run_sequence_device(frames10.data_ptr() + N, N, T, pos.data_ptr(), xs.data_ptr(), df.data_ptr(), cap,
+                                  show.data_ptr(), N, cuda_stream=st)
+        ms = timed(run, reps)
+        s.sequence_status()
+        sp = int(pos.to(torch.int64).sum().item())
+        alg = algorithmic_bytes(T, sp, N, k_n)
+        gbs = alg / (ms * 1e-3) / 1e9
+        out.append({"name": name, "frames": T, "us_per_frame": 1e3 * ms / T, "frames_per_s": T / (ms * 1e-3),
+                    "realised_c": sp / (T * N), "algorithmic_GBps": gbs, "frac": gbs / peak, "bytes_model": note,
+                    "launches_per_sequence": (s.launch_count() - l0) // (reps + 1)})
+        s.close()
+    del show
+
+    # ---- config 5: eight independent 3840x2160 streams, stream sid on rank sid mod world
+    mine = cvs.sharding.my_streams(C5_STREAMS, rank, world)
+    T5 = C5_FRAMES
+    cap5 = N4K // 4
+    pos5 = torch.zeros(T5, dtype=torch.int32, device=dev)
+    xs5 = xs[:T5 * cap5] if xs.numel() >= T5 * cap5 else torch.empty(T5 * cap5, dtype=torch.int32, device=dev)
+    df5 = df[:T5 * cap5] if df.numel() >= T5 * cap5 else torch.empty(T5 * cap5, dtype=torch.uint8, device=dev)
+    st4 = []
+    for sid in mine:
+        fr = device_sequence(W4K, H4K, T5, C5_DENSITY, cvs.sharding.stream_seed(BASE_SEED, sid))
+        torch.cuda.synchronize()
+        st4.append((sid, fr, cvs.Stream(W4K, H4K, fr[:N4K].cpu().numpy(), threshold=THR, device=local, max_sequence=T5)))
+
+    def run5():
+        for sid, fr, s in st4:
+            s.run_sequence_device(fr.data_ptr() + N4K, N4K, T5, pos5.data_ptr(), xs5.data_ptr(), df5.data_ptr(), cap5,
+                                  cuda_stream=st)
+    run5()
+    torch.cuda.synchronize()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        run5()
+    b.record()
+    barrier()
+    ms5 = a.elapsed_time(b) / reps
+    sp5 = 0
+    for sid, fr, s in st4:
+        s.sequence_status()
+    if st4:
+        sp5 = int(pos5.to(torch.int64).sum().item()) * len(st4)  # pos5 holds the last stream's counts; same density everywhere
+    sec5, (nfr5, sp5) = cvs.sharding.reduce_job(ms5 * 1e-3, [T5 * len(st4), sp5], dev)
+    alg5 = algorithmic_bytes(nfr5, sp5, N4K, 2.0)
+    per_gpu = alg5 / sec5 / 1e9 / world
+    out.append({"name": "config5_8x3840x2160_streams", "streams": C5_STREAMS, "streams_per_gpu": len(mine) if world > 1 else C5_STREAMS,
+                "frames_per_stream": T5, "density_ppm": C5_DENSITY, "frames_per_s": nfr5 / sec5,
+                "us_per_frame_per_gpu": 1e6 * sec5 / max(1, T5 * len(mine)), "realised_c": sp5 / max(1, nfr5 * N4K),
+                "algorithmic_GBps_per_gpu": per_gpu, "frac": per_gpu / peak,
+                "bytes_model": "(2 + 6c) N at 3840x2160; whole-job 4K frames/s = frames of all ranks / max-over-ranks device time"})
+    for sid, fr, s in st4:
+        s.close()
+    return out
+
+
+def e2e_run(cvs, torch, args, seqs, local, barrier):
+    """frames/s through cvs_submit_io/cvs_wait with HOST frames: per frame an H2D of N bytes from pinned memory and a
     D2H of the count + payload.  The host ring of each density holds R consecutive frames walked back and forth so
-    that consecutive submissions are always one synthetic step apart."""
+    that consecutive submissions are always one synthetic step apart.  The three camera streams of the GPU are
+    submitted round-robin, so the H2D of one overlaps the payload D2H of another."""
     R = args.e2e_ring
     frames_per_density = args.e2e_frames
     rings = []
@@ -349,15 +518,14 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
         base = src[:N].cpu().numpy()
         s = cvs.Stream(W, H, base, threshold=THR, device=local)
         out = [(cvs.alloc_host(N + 32), cvs.alloc_host(4 * N + 32), (C.c_uint * 1)()) for _ in range(4)]
-        rings.append({"hb": hb, "stream": s, "out": out})
+        rings.append({"hb": hb, "stream": s, "out": out, "pending": [], "base": base})
     order = list(range(R)) + list(range(R - 2, 0, -1))
 
-    def run(nframes, count):
+    def run(nframes):
         d2h = 0
-        for q in rings:
-            s, hb, out = q["stream"], q["hb"], q["out"]
-            pending = []
-            for i in range(nframes):
+        for i in range(nframes):
+            for q in rings:
+                s, hb, out, pending = q["stream"], q["hb"], q["out"], q["pending"]
                 fb, xb, pb = out[i % 4]
                 if len(pending) == 4:
                     tk, pp = pending.pop(0)
@@ -366,27 +534,53 @@ def e2e_run(cvs, torch, dist, args, seqs, local, world, barrier):
                 # frames stay in the pinned capture ring; the payload bytes go to the slot's own pinned buffer
                 src = order[i % len(order)]
                 pending.append((s.submit_io_raw(hb.ptr + src * N, fb.ptr, None, "", C.addressof(pb), xb.ptr), pb))
-            for tk, pp in pending:
-                s.wait(tk)
+        for q in rings:
+            for tk, pp in q["pending"]:
+                q["stream"].wait(tk)
                 d2h += 4 + 5 * pp[0]
+            q["pending"].clear()
         return d2h
 
-    run(min(8, frames_per_density), False)
+    run(min(8, frames_per_density))
     launches0 = sum(q["stream"].launch_count() for q in rings)
     barrier()
     t0 = time.perf_counter()
-    d2h = run(frames_per_density, True)
+    d2h = run(frames_per_density)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     nfr = frames_per_density * len(rings)
     launches = sum(q["stream"].launch_count() for q in rings) - launches0
     dt, (nfr, d2h, launches) = cvs.sharding.reduce_job(dt, [nfr, d2h, launches], torch.device("cuda", local))
-    tm = rings[1]["stream"].timing()
     res = {"value": nfr / dt, "unit": "frames/s", "h2d_bytes_per_step": N * nfr, "d2h_bytes_per_step": d2h,
            "frames": nfr, "seconds": dt, "gpu_launches": launches,
            "note": "one e2e step = %d frames per density x 3 densities per GPU through cvs_submit_io/cvs_wait from a "
-                   "pinned host ring" % frames_per_density,
-           "last_frame_us": tm}
+                   "pinned host ring, the three streams submitted round-robin" % frames_per_density}
+
+    # ---- the synchronous drop-in call (cvs_exec: what the unchanged server.cpp:139 does), one stream at a time
+    nsync = min(args.sync_frames, frames_per_density)
+    per = []
+    t_all, f_all = 0.0, 0
+    for q, sq in zip(rings, seqs):
+        s, hb = q["stream"], q["hb"]
+        s.reset(q["base"])
+        fb, xb, pb = q["out"][0]
+        src = hb.array()
+        # cvs_exec works in place on the frame buffer (kernels.cu:522): copy the captured frame into it first, as the
+        # capture thread does; that host copy is outside the timed call
+        times = []
+        for i in range(nsync):
+            k = order[i % len(order)]
+            fb.array()[:N] = src[k * N:(k + 1) * N]
+            t1 = time.perf_counter()
+            s.exec_raw(fb.ptr, None, "", pb, xb.ptr)
+            times.append(time.perf_counter() - t1)
+        tm = s.timing()
+        tt = float(np.sum(times[2:]))
+        t_all += tt
+        f_all += len(times) - 2
+        per.append({"density_ppm": sq["d"], "frames_per_s": (len(times) - 2) / tt, "last_frame_us": tm})
+    res["sync_exec"] = {"value": f_all / t_all, "unit": "frames/s", "per_density": per,
+                        "note": "cvs_exec (synchronous H2D + kernels + D2H per call, pinned buffers), host clock around the call"}
     for q in rings:
         q["stream"].close()
     return res
@@ -402,14 +596,16 @@ def main():
     ap.add_argument("--frames", type=int, default=SEQ_FRAMES, help="frames per sequence")
     ap.add_argument("--e2e-frames", type=int, default=300, help="frames per density in the end-to-end leg")
     ap.add_argument("--e2e-ring", type=int, default=16)
+    ap.add_argument("--sync-frames", type=int, default=60, help="frames per density through the synchronous cvs_exec")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side workloads (configs 3, 4, 5)")
     ap.add_argument("--ref-seconds", type=float, default=20.0, help="--impl reference: CPU seconds over all steps")
     ap.add_argument("--width", type=int, default=W, help="frame width (default: the 1080p headline workload)")
     ap.add_argument("--height", type=int, default=H)
     args = ap.parse_args()
     if (args.width, args.height) != (W, H):
-        # side workloads (e.g. BASELINE config 5's 3840x2160 streams); the headline stays 1080p
+        # other frame sizes for the headline loop (experiments); the driver runs the 1080p default
         W, H = args.width, args.height
         N = 3 * W * H
         METRIC = "%dx%d frames/sec (diff+compact, %d-frame sequences at 1%%/10%%/50%% change density)" % (W, H, args.frames)

@@ -10,7 +10,7 @@ call needs the built library and an sm_100 GPU and fails loudly otherwise.
 from .api import (CVSError, CUDACore, Stream, alloc_host, device_count, library_path, load_library,  # noqa: F401
                   MODE_NONE, MODE_HEAT_MAP, MODE_RED_BLACK, MODE_RED_OVERLAP, MODE_GRAY_WEIGHTED,
                   MODE_BINARIZE, MODE_GRAY_AVERAGE, MODE_BINARIZE_AVERAGE)
-from . import filters, sharding, synth  # noqa: F401
+from . import filters, sharding, synth, wire  # noqa: F401
 
 __all__ = ["CVSError", "CUDACore", "Stream", "alloc_host", "device_count", "library_path", "load_library",
-           "filters", "sharding", "synth"]
+           "filters", "sharding", "synth", "wire"]

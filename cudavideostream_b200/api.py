@@ -68,6 +68,12 @@ SIGNATURES = {
     "cvs_binarize_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "cvs_noise_filter_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _f32p, _vp]),
     "cvs_client_apply_device": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "cvs_wire_bound": (_sz, [C.c_int, C.c_int]),
+    "cvs_wire_size": (_sz, [_vp]),
+    "cvs_submit_wire": (C.c_int, [_vp, _vp, _vp, _vp, C.c_char_p, C.POINTER(C.c_uint64)]),
+    "cvs_wire_encode_device": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "cvs_wire_decode_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
+    "cvs_wire_decode_status": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cvs_synth_base_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, _vp]),
     "cvs_synth_next_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
 }
@@ -176,6 +182,12 @@ class Stream:
         t = C.c_uint64(0)
         _check(load_library().cvs_submit_io(self._h, frame_ptr, diff_ptr, show_ptr, text.encode(), pos_ptr, xs_ptr,
                                             C.byref(t)))
+        return t.value
+
+    def submit_wire_raw(self, frame_ptr: int, wire_ptr: int, show_ptr, text: str) -> int:
+        """cvs_submit_wire: the payload comes back as one compact CVW1 frame in wire_ptr (see cudavideostream_b200.wire)."""
+        t = C.c_uint64(0)
+        _check(load_library().cvs_submit_wire(self._h, frame_ptr, wire_ptr, show_ptr, text.encode(), C.byref(t)))
         return t.value
 
     def wait(self, ticket: int) -> None:

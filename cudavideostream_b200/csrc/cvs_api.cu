@@ -19,6 +19,7 @@
 
 #include "cvs_filter_kernels.cuh"
 #include "cvs_stream_kernel.cuh"
+#include "cvs_stream_ws.cuh"
 
 namespace {
 
@@ -113,6 +114,9 @@ struct Slot {
     unsigned int *d_pos = nullptr;
     uint8_t *d_show = nullptr;
     unsigned int *h_pos = nullptr; // pinned
+    uint32_t *d_starts = nullptr;     // compact wire format: entries before each tile (ntiles + 2 words), on first use
+    uint8_t *d_wire = nullptr;        // compact wire format: encoded frame when the caller's buffer is not mapped
+    uint8_t *u_wire = nullptr;        // caller's buffer of a cvs_submit_wire ticket (nullptr: reference-format ticket)
     unsigned int *d_status = nullptr; // StatusBits of this ticket's launches (cleared at submit)
     unsigned int *h_status = nullptr; // pinned copy, valid once ev_pos has fired
     cudaEvent_t ev_h2d0 = nullptr, ev_h2d1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_pos = nullptr,
@@ -169,6 +173,26 @@ StreamKernel pick_kernel(int mode, bool hi, bool refreg)
     }
 }
 
+template <int MODE>
+StreamKernel pick_ws_hr(bool hi, bool refreg)
+{
+    if (hi) return refreg ? cvs::k_stream_ws<MODE, true, true> : cvs::k_stream_ws<MODE, true, false>;
+    return refreg ? cvs::k_stream_ws<MODE, false, true> : cvs::k_stream_ws<MODE, false, false>;
+}
+StreamKernel pick_ws_kernel(int mode, bool hi, bool refreg)
+{
+    switch (mode) {
+    case 1: return pick_ws_hr<1>(hi, refreg);
+    case 2: return pick_ws_hr<2>(hi, refreg);
+    case 3: return pick_ws_hr<3>(hi, refreg);
+    case 4: return pick_ws_hr<4>(hi, refreg);
+    case 5: return pick_ws_hr<5>(hi, refreg);
+    case 6: return pick_ws_hr<6>(hi, refreg);
+    case 7: return pick_ws_hr<7>(hi, refreg);
+    default: return pick_ws_hr<0>(hi, refreg);
+    }
+}
+
 } // namespace
 
 struct cvs_stream_s {
@@ -211,6 +235,8 @@ struct cvs_stream_s {
     Slot slot[kSlots];
     int last_slot = -1; // slot of the most recently completed ticket (for cvs_get_timing)
     int occ_cache[8][2][2] = {}; // co-resident blocks per SM of each k_stream variant (0 = not queried yet)
+    int occ_ws[8][2][2] = {};    // same for k_stream_ws
+    bool use_ws = true;          // CVS_STREAM_KERNEL=v1 selects the one-group kernel (k_stream) for A/B measurements
     uint64_t next_ticket = 1;
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
@@ -363,24 +389,34 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         if (s) return s;
     }
 
-    // ---- geometry of the persistent launch
-    int G = cvs::kBlocksPerSM * h->sms;
-    if (G > cvs::kLook * cvs::kThreads) G = cvs::kLook * cvs::kThreads; // the look-back reads kLook predecessors per thread
+    // ---- geometry of the persistent launch: G co-resident blocks, each owning the same cps consecutive chunks of
+    //      every frame; frames larger than G * 512 chunks take nseg passes
+    const bool ws = h->use_ws;
+    int G = ws ? h->sms : cvs::kBlocksPerSM * h->sms;
+    const int look_max = ws ? 32 * cvs::kWsLook : cvs::kLook * cvs::kThreads; // predecessors the look-back can read
+    if (G > look_max) G = look_max;
     if ((uint32_t)G > h->nchunks) G = (int)h->nchunks;
     uint32_t nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
     uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
-    StreamKernel kern = pick_kernel(kmode, h->hi, refreg);
-    // ring depth: see nstages in k_stream
+    StreamKernel kern = ws ? pick_ws_kernel(kmode, h->hi, refreg) : pick_kernel(kmode, h->hi, refreg);
+    const int block_threads = ws ? cvs::kWsThreads : cvs::kThreads;
+    // ring depth: all four stages when the reference lives in registers (measured +5 % at 1080p), three when it goes
+    // through L2 (a deeper prefetch measured 17 % slower at 3840x2160 with k_stream); fewer if shared memory is short
     int nstages = refreg ? cvs::kStages : cvs::kStages - 1;
 #ifdef CVS_PROFILING
     if (h->stages >= 2 && h->stages <= cvs::kStages) nstages = h->stages;
 #endif
-    const int smem_bytes = cvs::SmemLayout::total(nstages);
-    int &occ = h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
+    int smem_max = 0;
+    CU_TRY(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    auto smem_need = [&](int ns) { return ws ? (int)cvs::WsLayout::total(cps, (uint32_t)ns) : cvs::SmemLayout::total(ns); };
+    while (nstages > 2 && smem_need(nstages) > smem_max) nstages--;
+    const int smem_bytes = smem_need(nstages);
+    if (smem_bytes > smem_max) return fail(CVS_ERR_INTERNAL, "stream kernel needs %d bytes of shared memory, device has %d", smem_bytes, smem_max);
+    int &occ = ws ? h->occ_ws[kmode][h->hi ? 1 : 0][refreg ? 1 : 0] : h->occ_cache[kmode][h->hi ? 1 : 0][refreg ? 1 : 0];
     if (occ == 0) { // first launch of this variant on this handle
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, cvs::kThreads, smem_bytes));
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block_threads, smem_bytes));
     }
     if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
     if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
@@ -454,8 +490,7 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         p.debug = h->debug;
         p.status = d_status;
         void *args[] = {&p};
-        CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(cvs::kThreads), args,
-                                           (size_t)smem_bytes, st));
+        CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
         h->launches++;
 
         if (binarize) {
@@ -566,6 +601,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
     if (const char *sg = getenv("CVS_STAGES")) h->stages = atoi(sg);
 #endif
+    if (const char *kk = getenv("CVS_STREAM_KERNEL")) h->use_ws = strcmp(kk, "v1") != 0; // both kernels are bit-exact
     if (const char *pp = getenv("CVS_PAYLOAD_PUSH")) h->push_payload = atoi(pp) != 0;
     if (const char *sp = getenv("CVS_EGRESS_SPECULATE")) h->speculate = atoi(sp) != 0;
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
@@ -650,6 +686,8 @@ cvs_status cvs_destroy(cvs_handle h)
         cudaFreeHost(s.h_pos);
         cudaFree(s.d_status);
         cudaFreeHost(s.h_status);
+        cudaFree(s.d_starts);
+        cudaFree(s.d_wire);
         cudaEvent_t evs[] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.ev_p0, s.ev_done};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
@@ -692,14 +730,21 @@ cvs_status cvs_free_host(void *ptr)
     return CVS_OK;
 }
 
-cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
-                         unsigned int *pos, int *xs, uint64_t *ticket)
+// common body of cvs_submit / cvs_submit_io (reference-format payload into diff_out / xs / pos) and cvs_submit_wire
+// (wire_out != nullptr: compact "CVW1" frame, see cvs_filter_kernels.cuh)
+static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
+                                unsigned int *pos, int *xs, uint8_t *wire_out, uint64_t *ticket)
 {
     cvs_status st = check_handle(h);
     if (st) return st;
-    if (!frame || !diff_out || !pos || !xs || !ticket) return fail(CVS_ERR_INVALID, "null argument");
+    if (!frame || !ticket || (!wire_out && (!diff_out || !pos || !xs))) return fail(CVS_ERR_INVALID, "null argument");
     Slot &s = h->slot[h->next_ticket % kSlots];
     if (s.busy) return fail(CVS_ERR_INVALID, "%d tickets are already outstanding; cvs_wait the oldest first", kSlots);
+    const uint32_t ntiles = (h->N + cvs::kWireTile - 1) / cvs::kWireTile;
+    if (wire_out && !s.d_starts) {
+        CU_TRY(cudaMalloc(&s.d_starts, (size_t)(ntiles + 2) * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&s.d_wire, cvs_wire_bound(h->width, h->height)));
+    }
 
     const double th0 = h->trace ? host_us() : 0;
     // H2D (kernels.cu:461)
@@ -736,16 +781,32 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     void *dev_diff = nullptr, *dev_xs = nullptr;
     s.spec = 0;
     s.pushed = false;
+    s.u_wire = wire_out;
+    if (wire_out) {
+        // compact wire format: two small kernels turn the payload into (tile counts, offsets, values) and store the
+        // encoded frame -- its size depends on the count, which only the device knows yet -- straight into the
+        // caller's pinned buffer; a pageable buffer gets the bytes from s.d_wire in cvs_wait
+        void *dev_wire = nullptr;
+        s.pushed = mapped_device_pointer(wire_out, &dev_wire) && ((uintptr_t)dev_wire % 16 == 0);
+        cvs::k_wire_bounds<<<(ntiles + 256) / 256, 256, 0, h->s_d2h>>>(s.d_xs, s.d_pos, cap, ntiles, s.d_starts);
+        CU_TRY(cudaGetLastError());
+        cvs::k_wire_pack<<<2 * h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, cap, ntiles, s.d_starts,
+                                                         s.pushed ? (uint8_t *)dev_wire : s.d_wire);
+        CU_TRY(cudaGetLastError());
+        h->launches += 2;
+    }
     const uint32_t spec_lo = h->N / 64u < 262144u ? h->N / 64u : 262144u; // ~1.3 MB of payload at 1080p
     // only with a prediction from a previous frame, and never more entries than the caller's buffers hold (N)
-    if (h->speculate && diff_out != frame && h->pred != 0 && h->pred >= spec_lo && h->pred <= h->N / 4u) {
+    if (wire_out) {
+        // nothing else to fetch: the encoded frame carries the count
+    } else if (h->speculate && diff_out != frame && h->pred != 0 && h->pred >= spec_lo && h->pred <= h->N / 4u) {
         const size_t guess = round_up(h->pred, 4);
         s.spec = (uint32_t)(guess > h->N ? h->N : guess);
     } else {
         s.pushed = h->push_payload && mapped_device_pointer(diff_out, &dev_diff) && mapped_device_pointer(xs, &dev_xs) &&
                    ((uintptr_t)dev_diff % 16 == 0) && ((uintptr_t)dev_xs % 16 == 0);
     }
-    if (s.pushed) {
+    if (s.pushed && !wire_out) {
         cvs::k_payload_push<<<h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, (int *)dev_xs, (uint8_t *)dev_diff, cap);
         CU_TRY(cudaGetLastError());
         h->launches++;
@@ -767,6 +828,19 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
     s.u_pos = pos;
     *ticket = s.ticket;
     return CVS_OK;
+}
+
+cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
+                         unsigned int *pos, int *xs, uint64_t *ticket)
+{
+    return submit_common(h, frame, diff_out, show, text, pos, xs, nullptr, ticket);
+}
+
+cvs_status cvs_submit_wire(cvs_handle h, const uint8_t *frame, uint8_t *wire_out, uint8_t *show, const char *text,
+                           uint64_t *ticket)
+{
+    if (!wire_out) return fail(CVS_ERR_INVALID, "null argument");
+    return submit_common(h, frame, nullptr, show, text, nullptr, nullptr, wire_out, ticket);
 }
 
 cvs_status cvs_submit(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text, unsigned int *pos, int *xs,
@@ -792,15 +866,24 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
     // (on their own stream: s_d2h already holds the work of the younger tickets, and anything queued behind
     // it would make this call wait for them)
     const unsigned int have = s.spec; // entries already on the host
-    s.copied = n > have && !s.pushed;
-    if (s.copied) {
+    if (s.u_wire) {
+        s.copied = !s.pushed;
+        if (s.copied) { // pageable buffer: the encoded frame waits in device memory
+            const size_t cap_n = n > h->N ? h->N : n;
+            const size_t bytes = cvs::kWireHeader + cvs::wire_pad16((h->N + cvs::kWireTile - 1) / cvs::kWireTile) +
+                                 cvs::wire_pad16((uint32_t)cap_n) + cap_n;
+            CU_TRY(cudaMemcpyAsync(s.u_wire, s.d_wire, bytes, cudaMemcpyDeviceToHost, h->s_pay));
+            CU_TRY(cudaEventRecord(s.ev_done, h->s_pay));
+            CU_TRY(cudaEventSynchronize(s.ev_done));
+        }
+    } else if ((s.copied = n > have && !s.pushed)) {
         CU_TRY(cudaMemcpyAsync(s.u_frame + have, s.d_diff + have, n - have, cudaMemcpyDeviceToHost, h->s_pay));
         CU_TRY(cudaMemcpyAsync(s.u_xs + have, s.d_xs + have, (size_t)(n - have) * sizeof(int), cudaMemcpyDeviceToHost, h->s_pay));
         CU_TRY(cudaEventRecord(s.ev_done, h->s_pay));
         CU_TRY(cudaEventSynchronize(s.ev_done));
     }
     s.busy = false; // from here on nothing can fail: the slot may be reused
-    *s.u_pos = n;
+    if (s.u_pos) *s.u_pos = n;
     h->pred = n + (n / 16 > 16384 ? n / 16 : 16384); // change density is strongly correlated from frame to frame
     h->last_slot = (int)(ticket % kSlots);
     if (h->trace) { // CVS_TRACE=1: device timeline of every ticket on stderr (debug aid)
@@ -1029,6 +1112,69 @@ cvs_status cvs_client_apply_device(uint8_t *d_frame, const int *d_xs, const uint
     if (!d_frame || !d_xs || !d_diff || !d_pos) return fail(CVS_ERR_INVALID, "null argument");
     cvs::k_client_apply<<<sms * 4, 256, 0, (cudaStream_t)cuda_stream>>>(d_frame, d_xs, d_diff, d_pos, capacity);
     CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+size_t cvs_wire_bound(int width, int height)
+{
+    if (width <= 0 || height <= 0) return 0;
+    const uint64_t n = (uint64_t)3 * (uint64_t)width * (uint64_t)height;
+    const uint64_t ntiles = (n + cvs::kWireTile - 1) / cvs::kWireTile;
+    return (size_t)(cvs::kWireHeader + ((ntiles + 15) & ~15ull) + ((n + 15) & ~15ull) + n);
+}
+
+size_t cvs_wire_size(const uint8_t *wire)
+{
+    if (!wire) return 0;
+    uint32_t hd[4];
+    memcpy(hd, wire, sizeof hd);
+    if (hd[0] != cvs::kWireMagic || hd[3] != cvs::kWireTile) return 0;
+    return (size_t)cvs::kWireHeader + cvs::wire_pad16(hd[2]) + cvs::wire_pad16(hd[1]) + hd[1];
+}
+
+cvs_status cvs_wire_encode_device(const int *d_xs, const uint8_t *d_diff, const unsigned int *d_pos, size_t capacity,
+                                  int width, int height, uint32_t *d_scratch, uint8_t *d_wire, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_xs || !d_diff || !d_pos || !d_scratch || !d_wire || width <= 0 || height <= 0)
+        return fail(CVS_ERR_INVALID, "bad argument");
+    if (((uintptr_t)d_xs | (uintptr_t)d_diff | (uintptr_t)d_wire) & 15) return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height, ntiles = (n + cvs::kWireTile - 1) / cvs::kWireTile;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    cvs::k_wire_bounds<<<(ntiles + 256) / 256, 256, 0, s>>>(d_xs, d_pos, capacity, ntiles, d_scratch);
+    CU_TRY(cudaGetLastError());
+    cvs::k_wire_pack<<<2 * sms, 256, 0, s>>>(d_xs, d_diff, d_pos, capacity, ntiles, d_scratch, d_wire);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_wire_decode_device(const uint8_t *d_wire, uint32_t *d_scratch, uint8_t *d_frame, int *d_xs, uint8_t *d_diff,
+                                  unsigned int *d_pos, int width, int height, void *cuda_stream)
+{
+    int sms = 0;
+    cvs_status st = filter_common(sms);
+    if (st) return st;
+    if (!d_wire || !d_scratch || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    if ((uintptr_t)d_wire & 15) return fail(CVS_ERR_ALIGN, "16-byte alignment required");
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height, ntiles = (n + cvs::kWireTile - 1) / cvs::kWireTile;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    cvs::k_wire_scan<<<1, 1024, 0, s>>>(d_wire, ntiles, d_scratch);
+    CU_TRY(cudaGetLastError());
+    cvs::k_wire_apply<<<4 * sms, 256, 0, s>>>(d_wire, ntiles, d_scratch, d_frame, d_xs, d_diff, d_pos);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int height, void *cuda_stream)
+{
+    if (!d_scratch || width <= 0 || height <= 0) return fail(CVS_ERR_INVALID, "bad argument");
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height, ntiles = (n + cvs::kWireTile - 1) / cvs::kWireTile;
+    uint32_t flag = 0;
+    CU_TRY(cudaMemcpyAsync(&flag, d_scratch + ntiles + 1, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+    if (flag) return fail(CVS_ERR_INVALID, "encoded frame is inconsistent (magic, geometry or counts): nothing was applied");
     return CVS_OK;
 }
 

@@ -401,6 +401,151 @@ __global__ void __launch_bounds__(256) k_payload_push(const int *__restrict__ xs
 }
 
 // ------------------------------------------------------------------------------------------------
+// Opt-in compact wire format "CVW1" (SURVEY.md section 8f row 3).  The reference sends, per frame, u32 pos,
+// i32 xs[pos], u8 diff[pos] (server/src/threads.cpp:229-231, read back by client/opencv.cpp:52-66): 5 bytes per
+// entry.  Because xs is ascending, the index can be sent as (tile, offset): the frame is cut into tiles of
+// kWireTile = 192 bytes (64 pixels), a tile's entry count fits one byte (0..192) and so does the offset inside the
+// tile.  Encoded frame (little endian):
+//     u32 magic "CVW1", u32 pos, u32 ntiles, u32 tile            16-byte header
+//     u8  count[ntiles]   (padded to a multiple of 16)
+//     u8  off[pos]        (padded to a multiple of 16)            offset of entry i inside its tile
+//     u8  diff[pos]                                               the reference's value bytes, unchanged
+// = 16 + N/192 + 2 pos bytes instead of 4 + 5 pos.  Encoding is two small kernels over the payload the stream kernel
+// left in device memory; they store 16 bytes per thread straight into the caller's (mapped, pinned) buffer.
+// Decoding (client side): exclusive scan of the counts, then one warp per tile.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kWireTile = 192;
+constexpr uint32_t kWireMagic = 0x31575643u; // "CVW1"
+constexpr uint32_t kWireHeader = 16;
+
+__host__ __device__ __forceinline__ uint32_t wire_pad16(uint32_t v) { return (v + 15u) & ~15u; }
+
+// starts[t] = number of entries with index < t * kWireTile, t = 0..ntiles (xs ascending: one binary search each)
+__global__ void __launch_bounds__(256) k_wire_bounds(const int *__restrict__ xs, const unsigned int *__restrict__ pos,
+                                                     size_t capacity, uint32_t ntiles, uint32_t *__restrict__ starts)
+{
+    uint32_t n = *pos;
+    if (n > capacity) n = (uint32_t)capacity;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= ntiles; t += gridDim.x * blockDim.x) {
+        const int key = (int)(t * kWireTile);
+        uint32_t lo = 0, hi = n;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(xs + mid) < key) lo = mid + 1;
+            else hi = mid;
+        }
+        starts[t] = lo;
+    }
+}
+
+// header, per-tile counts and the (offset, value) bytes; `out` may be mapped host memory (16-byte aligned)
+__global__ void __launch_bounds__(256) k_wire_pack(const int *__restrict__ xs, const uint8_t *__restrict__ diff,
+                                                   const unsigned int *__restrict__ pos, size_t capacity, uint32_t ntiles,
+                                                   const uint32_t *__restrict__ starts, uint8_t *out)
+{
+    uint32_t n = *pos;
+    if (n > capacity) n = (uint32_t)capacity;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    if (tid == 0) *reinterpret_cast<uint4 *>(out) = make_uint4(kWireMagic, n, ntiles, kWireTile);
+    uint8_t *cnt = out + kWireHeader;
+    uint8_t *off = cnt + wire_pad16(ntiles);
+    uint8_t *val = off + wire_pad16(n);
+    // counts: 16 tiles per thread
+    for (uint32_t t0 = 16 * tid; t0 < ntiles; t0 += 16 * nt) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t t = t0 + j;
+            const uint32_t c = t < ntiles ? starts[t + 1] - starts[t] : 0u;
+            w[j >> 2] |= c << (8 * (j & 3));
+        }
+        *reinterpret_cast<uint4 *>(cnt + t0) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    // entries: 16 per thread
+    for (uint32_t i0 = 16 * tid; i0 < n; i0 += 16 * nt) {
+        uint32_t w[4] = {0, 0, 0, 0};
+        if (i0 + 16 <= n) {
+            const int4 *xp = reinterpret_cast<const int4 *>(xs + i0);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int4 x = __ldg(xp + q);
+                w[q] = ((uint32_t)x.x % kWireTile) | (((uint32_t)x.y % kWireTile) << 8) | (((uint32_t)x.z % kWireTile) << 16) |
+                       (((uint32_t)x.w % kWireTile) << 24);
+            }
+            *reinterpret_cast<uint4 *>(val + i0) = __ldg(reinterpret_cast<const uint4 *>(diff + i0));
+        } else {
+            for (uint32_t j = 0; i0 + j < n; j++) {
+                w[j >> 2] |= ((uint32_t)xs[i0 + j] % kWireTile) << (8 * (j & 3));
+                val[i0 + j] = diff[i0 + j];
+            }
+        }
+        *reinterpret_cast<uint4 *>(off + i0) = make_uint4(w[0], w[1], w[2], w[3]); // the off region is padded to 16
+    }
+}
+
+// client: exclusive scan of the per-tile counts of one encoded frame -> starts[0..ntiles], one 1024-thread block.
+// starts[ntiles + 1] = 0 when header and counts are consistent with the frame geometry, else 1.
+__global__ void __launch_bounds__(1024) k_wire_scan(const uint8_t *__restrict__ wire, uint32_t ntiles_expected,
+                                                    uint32_t *__restrict__ starts)
+{
+    __shared__ uint32_t wsum[32];
+    const uint4 hd = *reinterpret_cast<const uint4 *>(wire);
+    const uint32_t ntiles = ntiles_expected;
+    const bool header_ok = hd.x == kWireMagic && hd.z == ntiles_expected && hd.w == kWireTile;
+    const uint8_t *cnt = wire + kWireHeader;
+    const uint32_t per = (ntiles + 1023u) / 1024u;
+    const uint32_t t0 = threadIdx.x * per;
+    uint32_t mine = 0;
+    for (uint32_t j = 0; j < per; j++)
+        if (t0 + j < ntiles) mine += cnt[t0 + j];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t incl = warp_incl_scan(mine, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = wsum[lane];
+        const uint32_t iv = warp_incl_scan(v, lane);
+        wsum[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = wsum[warp] + incl - mine;
+    for (uint32_t j = 0; j < per; j++)
+        if (t0 + j < ntiles) {
+            starts[t0 + j] = run;
+            run += cnt[t0 + j];
+        }
+    if (threadIdx.x == 1023) {
+        starts[ntiles] = run;
+        starts[ntiles + 1] = (header_ok && run == hd.y) ? 0u : 1u;
+    }
+}
+
+// client: frame[x] += diff (client/opencv.cpp:64-66) and/or the reference-format payload back, one warp per tile
+__global__ void __launch_bounds__(256) k_wire_apply(const uint8_t *__restrict__ wire, uint32_t ntiles,
+                                                    const uint32_t *__restrict__ starts, uint8_t *frame, int *xs_out,
+                                                    uint8_t *diff_out, unsigned int *pos_out)
+{
+    if (starts[ntiles + 1]) return; // inconsistent frame: nothing is applied, the host reports it
+    const uint32_t n = starts[ntiles];
+    const uint8_t *cnt = wire + kWireHeader;
+    const uint8_t *off = cnt + wire_pad16(ntiles);
+    const uint8_t *val = off + wire_pad16(n);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    if (pos_out && blockIdx.x == 0 && threadIdx.x == 0) *pos_out = n;
+    for (uint32_t t = w; t < ntiles; t += nw) {
+        const uint32_t c = cnt[t], s0 = starts[t];
+        for (uint32_t j = lane; j < c; j += 32) {
+            const uint32_t x = t * kWireTile + off[s0 + j];
+            const uint8_t d = val[s0 + j];
+            if (frame) frame[x] = (uint8_t)(frame[x] + d);
+            if (xs_out) xs_out[s0 + j] = (int)x;
+            if (diff_out) diff_out[s0 + j] = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // synthetic camera; numpy twin: cudavideostream_b200/synth.py
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint8_t synth_base_byte(uint64_t seed, uint32_t i, int width, int height)

@@ -1,0 +1,455 @@
+// cvs_stream_ws.cuh -- the fused hot path as a WARP-SPECIALISED persistent kernel (round 2).
+//
+// Same work, same results and same data layout as k_stream (cvs_stream_kernel.cuh: thresholded difference +
+// negative feedback + ordered compaction (+ one display filter) over a sequence of frames, replacing kernel2,
+// server/src/kernels.cu:289-334, and its CPU twin tests/cuda_streaming/test.cu:560-576), but a block is split into
+// two groups of warps that only meet through mbarriers:
+//
+//   FRONT warps (0..15)   own the reference bytes (in registers when a frame fits one pass of the grid) and run
+//                         the per-word pass of step q: pixels out of the TMA ring, flags, 96-bit change mask,
+//                         difference bytes parked in the thread's own 96 bytes of the ring stage, negative feedback,
+//                         display filter.  They leave (mask, count) per chunk and the warp totals in shared memory,
+//                         arrive on fdone[stage] and go straight on to step q+1 -- no block barrier, no look-back.
+//   BACK warps (16..31)   back warp w emits the entries of front warp w's 32 chunks: it waits for fdone[stage],
+//                         scans the counts, waits for the block's global offset and stages + flushes (sparse) or
+//                         stores cooperatively (dense) exactly as k_stream does.  The LAST back warp also owns the
+//                         cross-block exchange: it publishes the block total of the step and sums the predecessors'
+//                         descriptors (one-round look-back) before it turns to its own emission.  The last back
+//                         warp to finish a stage re-arms it and issues the bulk copy of step q+nstages.
+//
+// Why: k_stream runs one 512-thread block per SM (the frame gives an SM only 438 chunks at 1080p, and 112
+// registers per thread leave room for nothing else), i.e. 3.5 warps per scheduler, and ncu shows 1.0 eligible warp
+// per cycle, 52 % issue utilisation, 18 % of warp time at the one block barrier.  Splitting the step doubles the
+// warps that can issue (the pass of step q+1 overlaps look-back latency and emission of step q), removes the block
+// barrier, and setmaxnreg moves registers from the back warps (which need few) to the front warps.
+#pragma once
+#include "cvs_stream_kernel.cuh"
+
+namespace cvs {
+
+constexpr int kWsFrontWarps = 16;
+constexpr int kWsBackWarps = 16;
+constexpr int kWsThreads = 32 * (kWsFrontWarps + kWsBackWarps); // 1024
+constexpr int kWsFrontThreads = 32 * kWsFrontWarps;             // chunks per block per step (= kThreads)
+constexpr int kWsLook = 5;                                      // descriptors a lane of the look-back warp reads: G <= 160
+#ifndef CVS_WS_FRONT_REGS
+#define CVS_WS_FRONT_REGS 80
+#endif
+#ifndef CVS_WS_BACK_REGS
+#define CVS_WS_BACK_REGS 48
+#endif
+static_assert(kWsFrontThreads == kThreads, "front threads own one chunk each, like k_stream's threads");
+static_assert(512 * CVS_WS_FRONT_REGS + 512 * CVS_WS_BACK_REGS <= 65536, "register file");
+
+// dynamic shared memory of k_stream_ws (bytes).  Stage size and mask stride follow the chunks per block of the
+// launch (cps), so four stages fit next to the mask queue at 1080p / 3840x2160 (cps = 438).
+struct WsLayout {
+    static constexpr int lut = 0;                                      // 768 words
+    static constexpr int hist = lut + 768 * 4;                         // 256 words
+    static constexpr int bar_full = hist + 256 * 4;                    // kStages mbarriers: bulk copy landed
+    static constexpr int bar_fdone = bar_full + 8 * 8;                 // kStages mbarriers: front warps done with the step
+    static constexpr int bar_base = bar_fdone + 8 * 8;                 // kStages mbarriers: global offset of the block known
+    static constexpr int done = bar_base + 8 * 8;                      // kStages words: back warps finished with the stage
+    static constexpr int base = done + 8 * 4;                          // kStages words: global rank of the block's first entry
+    static constexpr int wtot = base + 8 * 4;                          // kStages x 16 words: entries per front warp
+    static constexpr int sxs = wtot + 8 * 16 * 4;                      // kWsBackWarps * kXsHalves uint16
+    static constexpr int sd = sxs + kWsBackWarps * SmemLayout::kXsHalves * 2;
+    static constexpr int msk = (sd + kWsBackWarps * SmemLayout::kSdBytes + 127) / 128 * 128; // nstages * msk_stride
+    static __host__ __device__ constexpr uint32_t msk_stride(uint32_t cps) { return (cps + 31u) / 32u * 32u * 16u; }
+    static __host__ __device__ constexpr uint32_t stage_bytes(uint32_t cps) { return (cps * kChunkBytes + 127u) / 128u * 128u; }
+    static __host__ __device__ constexpr uint32_t stage0(uint32_t cps, uint32_t nstages) { return msk + nstages * msk_stride(cps); }
+    static __host__ __device__ constexpr uint32_t total(uint32_t cps, uint32_t nstages)
+    {
+        return stage0(cps, nstages) + nstages * stage_bytes(cps);
+    }
+};
+static_assert(WsLayout::bar_full % 8 == 0 && WsLayout::sxs % 16 == 0 && WsLayout::sd % 16 == 0, "alignment");
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int MODE, bool HI, bool REFREG>
+__global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t b = blockIdx.x, G = gridDim.x;
+    const uint32_t N = p.nbytes;
+    const uint32_t nsteps = (uint32_t)p.nframes * p.nseg;
+    const uint32_t nstages = p.nstages;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t msk_stride = WsLayout::msk_stride(p.cps), stage_bytes = WsLayout::stage_bytes(p.cps);
+    const uint32_t stage_addr = smem0 + WsLayout::stage0(p.cps, nstages);
+    const uint32_t msk_addr = smem0 + WsLayout::msk;
+    const uint32_t bar_full = smem0 + WsLayout::bar_full, bar_fdone = smem0 + WsLayout::bar_fdone,
+                   bar_base = smem0 + WsLayout::bar_base;
+    uint32_t *done = reinterpret_cast<uint32_t *>(smem + WsLayout::done);
+    uint32_t *sbase = reinterpret_cast<uint32_t *>(smem + WsLayout::base);
+    uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + WsLayout::wtot);
+    constexpr bool kBinarize = (MODE == kModeBinarize || MODE == kModeBinarizeAvg);
+    constexpr bool kGrayW = (MODE == kModeGrayWeighted || MODE == kModeBinarize);
+
+    // slice of this block in segment s: byte offset and byte count of the bulk copy
+    auto slice = [&](uint32_t s, uint32_t &off, uint32_t &bytes) {
+        uint64_t c0 = ((uint64_t)s * G + b) * p.cps;
+        uint64_t o = c0 * kChunkBytes;
+        if (o >= p.nbytes16) { off = 0; bytes = 0; return; }
+        uint64_t e = o + (uint64_t)p.cps * kChunkBytes;
+        if (e > p.nbytes16) e = p.nbytes16;
+        off = (uint32_t)o;
+        bytes = (uint32_t)(e - o);
+    };
+    // one thread: refill ring stage st with the slice of step q
+    auto issue = [&](uint32_t q, uint32_t st) {
+        const uint32_t t = REFREG ? q : q / p.nseg, s = REFREG ? 0u : q - t * p.nseg;
+        uint32_t off, bytes;
+        slice(s, off, bytes);
+        if (bytes) {
+            const uint64_t pol = l2_policy_evict_first();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // parked bytes were written through the generic proxy
+            mbar_expect_tx(bar_full + 8 * st, bytes);
+            bulk_g2s(stage_addr + st * stage_bytes, p.frames + (size_t)t * p.frame_stride + off, bytes, bar_full + 8 * st, pol);
+        }
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < kStages; i++) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_fdone + 8 * i, kWsFrontWarps);
+            mbar_init(bar_base + 8 * i, 1);
+            done[i] = 0;
+        }
+        mbar_init_fence();
+    }
+    if (MODE == kModeHeat) {
+        uint32_t *slut = reinterpret_cast<uint32_t *>(smem + WsLayout::lut);
+        for (uint32_t i = tid; i < 766; i += kWsThreads) slut[i] = p.heat_lut[i];
+    }
+    if (kBinarize) {
+        uint32_t *shist = reinterpret_cast<uint32_t *>(smem + WsLayout::hist);
+        for (uint32_t i = tid; i < 256; i += kWsThreads) shist[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (uint32_t q = 0; q < nstages && q < nsteps; q++) issue(q, q);
+
+    // a spin wait that gave up once stops every later wait of the thread (the launch must terminate); the status word
+    // tells the host
+    bool tripped = false;
+    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
+        if (!tripped && !mbar_wait(bar, parity)) {
+            tripped = true;
+            atomicOr(p.status, kStatusWatchdog);
+        }
+    };
+
+    if (warp < (uint32_t)kWsFrontWarps) {
+        // =====================================================================================================
+        // FRONT: the per-word pass
+        // =====================================================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CVS_WS_FRONT_REGS));
+        uint32_t *slut = reinterpret_cast<uint32_t *>(smem + WsLayout::lut);
+        uint32_t *shist = reinterpret_cast<uint32_t *>(smem + WsLayout::hist);
+        // bank-conflict-free 16-byte shared accesses: lanes with bit 2 set keep their two 48-byte pixel groups in
+        // swapped order ("slot" order), see k_stream
+        const uint32_t sw = ((lane >> 2) & 1u) * (uint32_t)kGroupBytes;
+        auto voff = [&](int v) -> uint32_t { return v < 3 ? 16u * v + sw : 16u * v - sw; };
+        uint32_t r[kChunkWords];
+        const uint64_t keep = l2_policy_evict_last();
+        bool dirty = false;
+        uint32_t coff = 0, nv = 0, sbytes = 0;
+        auto geometry = [&](uint32_t s) {
+            uint32_t soff;
+            slice(s, soff, sbytes);
+            uint64_t c = ((uint64_t)s * G + b) * p.cps + tid;
+            bool ok = tid < p.cps && c < p.nchunks;
+            coff = ok ? (uint32_t)(c * kChunkBytes) : 0u;
+            nv = ok ? min(N - coff, (uint32_t)kChunkBytes) : 0u;
+        };
+        auto load_ref = [&]() {
+            if (nv) {
+#pragma unroll
+                for (int v = 0; v < kChunkWords / 4; v++) {
+                    uint4 a = ldg_keep(p.ref + coff + voff(v), keep);
+                    r[4 * v] = a.x; r[4 * v + 1] = a.y; r[4 * v + 2] = a.z; r[4 * v + 3] = a.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kChunkWords; k++) r[k] = 0;
+            }
+        };
+        auto store_ref = [&]() {
+#pragma unroll
+            for (int v = 0; v < kChunkWords / 4; v++)
+                stg_keep(p.ref + coff + voff(v), make_uint4(r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]), keep);
+        };
+        geometry(0);
+        if (REFREG) load_ref();
+
+        uint32_t phase = 0, st = 0, t = 0, s = 0;
+        for (uint32_t q = 0; q < nsteps; q++) {
+            if (!REFREG) {
+                geometry(s);
+                load_ref(); // L2 hit; issued before the wait on the frame slice
+            }
+            if (sbytes) {
+                wait_bar(bar_full + 8 * st, (phase >> st) & 1u);
+                phase ^= 1u << st;
+            }
+            const uint32_t myaddr = stage_addr + st * stage_bytes + tid * kChunkBytes;
+            uint32_t m[kMaskWords] = {0, 0, 0};
+            constexpr bool kStreamLoad = (MODE == kModeNone);
+            // the chunk that holds the end of the frame: bytes past N never differ (slot word k of the chunk)
+            auto clip_word = [&](int k, uint32_t cw) -> uint32_t {
+                const int vb = (int)nv - (int)(voff(k >> 2) + 4 * (k & 3));
+                const uint32_t vm = vb >= 4 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << (8 * vb)) - 1u));
+                return (cw & vm) | (r[k] & ~vm);
+            };
+            // one 16-byte vector of the chunk: flags -> change mask, difference bytes (parked), negative feedback
+            //                                                                              (test.cu:565-570)
+            auto pass_vector = [&](int v, const uint32_t (&cv)[4]) {
+                uint32_t dv[4];
+#pragma unroll
+                for (int h = 0; h < 4; h += 2) {
+                    const int k = 4 * v + h;
+                    const uint32_t f0 = changed80<HI>(absdiff4(cv[h], r[k]), p.addc);
+                    const uint32_t f1 = changed80<HI>(absdiff4(cv[h + 1], r[k + 1]), p.addc);
+                    const uint32_t g8 = __umulhi(f1 + (f0 >> 4), 0x20408100u);
+                    m[k >> 3] = __byte_perm(m[k >> 3], g8, ((k >> 1) & 3) == 0 ? 0x3214 : ((k >> 1) & 3) == 1 ? 0x3240
+                                                          : ((k >> 1) & 3) == 2 ? 0x3410 : 0x4210);
+                    dv[h] = sub4<true>(cv[h], r[k]);
+                    dv[h + 1] = sub4<true>(cv[h + 1], r[k + 1]);
+                    const uint32_t fm0 = spread80(f0), fm1 = spread80(f1);
+                    r[k] = (cv[h] & fm0) | (r[k] & ~fm0);
+                    r[k + 1] = (cv[h + 1] & fm1) | (r[k + 1] & ~fm1);
+                }
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(myaddr + voff(v)), "r"(dv[0]), "r"(dv[1]), "r"(dv[2]),
+                             "r"(dv[3])
+                             : "memory");
+            };
+
+            // display filter on the same registers (reference as it was BEFORE this frame), then the pass
+            if (MODE != kModeNone && nv) {
+#pragma unroll
+                for (int g = 0; g < kGroupsPerThread; g++) {
+                    const uint32_t gb = sw ? (uint32_t)(1 - g) * kGroupBytes : (uint32_t)g * kGroupBytes;
+                    const uint32_t goff = coff + gb;
+                    const uint32_t gnv = nv > gb ? min(nv - gb, (uint32_t)kGroupBytes) : 0u;
+                    if (gnv == 0) continue;
+                    uint32_t cg[kGroupWords], rg[kGroupWords], o[kGroupWords];
+#pragma unroll
+                    for (int v = 0; v < kGroupWords / 4; v++) {
+                        const uint4 x = lds128(myaddr + voff(g * (kGroupWords / 4) + v));
+                        cg[4 * v] = x.x; cg[4 * v + 1] = x.y; cg[4 * v + 2] = x.z; cg[4 * v + 3] = x.w;
+                    }
+                    if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
+#pragma unroll
+                        for (int k = 0; k < kGroupWords; k++) cg[k] = clip_word(g * kGroupWords + k, cg[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kGroupWords; k++) rg[k] = r[g * kGroupWords + k];
+                    if (MODE == kModeHeat) {
+                        uint32_t ad[kGroupWords];
+#pragma unroll
+                        for (int k = 0; k < kGroupWords; k++) ad[k] = absdiff4(cg[k], rg[k]);
+                        group_heat(ad, slut, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (MODE == kModeRedBlack || MODE == kModeRedOverlap) {
+                        uint32_t mk[kGroupWords];
+#pragma unroll
+                        for (int k = 0; k < kGroupWords; k++) mk[k] = changed80<HI>(absdiff4(cg[k], rg[k]), p.addc);
+                        group_red<MODE == kModeRedOverlap>(mk, rg, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (MODE == kModeGrayWeighted || MODE == kModeGrayAverage) {
+                        group_gray3<kGrayW>(cg, o);
+                        store_group(p.show + (size_t)t * p.show_stride + goff, o, gnv);
+                    } else if (kBinarize) {
+                        uint32_t g4[4];
+                        group_gray1<kGrayW>(cg, g4);
+                        const uint32_t npx = gnv / 3u;
+                        uint8_t *gdst = p.gray1 + (size_t)t * p.gray_stride + goff / 3u;
+                        if (npx == (uint32_t)kGroupPixels) stg_keep(gdst, make_uint4(g4[0], g4[1], g4[2], g4[3]), keep);
+#pragma unroll
+                        for (int px = 0; px < kGroupPixels; px++) {
+                            if ((uint32_t)px < npx) {
+                                uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                                if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
+                                atomicAdd(&shist[gv], 1u); // server.cpp:103-106
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < kGroupWords / 4; v++) {
+                        const uint32_t cv[4] = {cg[4 * v], cg[4 * v + 1], cg[4 * v + 2], cg[4 * v + 3]};
+                        pass_vector(g * (kGroupWords / 4) + v, cv);
+                    }
+                }
+            }
+            if (kStreamLoad && nv) {
+                uint4 nx = lds128(myaddr + voff(0));
+#pragma unroll
+                for (int v = 0; v < kChunkWords / 4; v++) {
+                    uint32_t cv[4] = {nx.x, nx.y, nx.z, nx.w};
+                    if (v + 1 < kChunkWords / 4) nx = lds128(myaddr + voff(v + 1));
+                    if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
+#pragma unroll
+                        for (int h = 0; h < 4; h++) cv[h] = clip_word(4 * v + h, cv[h]);
+                    }
+                    pass_vector(v, cv);
+                }
+            }
+            if (sw) { // slot order -> byte order: rotate the 96-bit mask by 48
+                const uint32_t n0 = __funnelshift_r(m[1], m[2], 16), n1 = __funnelshift_r(m[2], m[0], 16),
+                               n2 = __funnelshift_r(m[0], m[1], 16);
+                m[0] = n0; m[1] = n1; m[2] = n2;
+            }
+            if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) { // bytes past the end of the frame are never entries
+#pragma unroll
+                for (int w = 0; w < kMaskWords; w++) {
+                    const int vb = (int)nv - 32 * w;
+                    m[w] &= vb >= 32 ? 0xffffffffu : (vb <= 0 ? 0u : ((1u << vb) - 1u));
+                }
+            }
+            if (m[0] | m[1] | m[2]) {
+                if (REFREG) dirty = true;
+                else store_ref();
+            }
+            const uint32_t cnt = (uint32_t)__popc(m[0]) + (uint32_t)__popc(m[1]) + (uint32_t)__popc(m[2]);
+            // hand the step to the back warps: (mask, count) per chunk, entries of this warp
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(msk_addr + st * msk_stride + 16 * tid), "r"(m[0]), "r"(m[1]),
+                         "r"(m[2]), "r"(cnt)
+                         : "memory");
+            const uint32_t wsum = warp_add(cnt);
+            if (lane == 0) wtot[st * 16 + warp] = wsum;
+            if (kBinarize && s == p.nseg - 1) {
+                // histogram of the frame complete: flush and clear (front warps only: named barrier 1)
+                asm volatile("bar.sync 1, %0;" ::"n"(kWsFrontThreads) : "memory");
+                for (uint32_t i = tid; i < 256; i += kWsFrontThreads) {
+                    const uint32_t hv = shist[i];
+                    if (hv) atomicAdd(p.hist + (size_t)t * 256 + i, hv);
+                    shist[i] = 0;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kWsFrontThreads) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_fdone + 8 * st); // release: the warp's shared stores above are visible to the waiters
+            if (REFREG) ++t;
+            else if (++s == p.nseg) { s = 0; ++t; }
+            if (++st == nstages) st = 0;
+        }
+        if (REFREG && dirty) store_ref();
+    } else {
+        // =====================================================================================================
+        // BACK: block scan, cross-block look-back, emission of the (index, value) entries
+        // =====================================================================================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CVS_WS_BACK_REGS));
+        const uint32_t bw = warp - kWsFrontWarps;     // front warp whose chunks this warp emits
+        const uint32_t ftid = bw * 32 + lane;         // front thread whose chunk this lane emits
+        const bool scan_warp = bw == (uint32_t)kWsBackWarps - 1;
+        uint16_t *sxs = reinterpret_cast<uint16_t *>(smem + WsLayout::sxs) + bw * SmemLayout::kXsHalves;
+        uint8_t *sd = smem + WsLayout::sd + bw * SmemLayout::kSdBytes;
+        const uint32_t cap32 = p.cap > 0xffffffffull ? 0xffffffffu : (uint32_t)p.cap;
+
+        uint32_t ph_f = 0, ph_b = 0, st = 0, t = 0, s = 0;
+        for (uint32_t q = 0; q < nsteps; q++) {
+            // byte offset of lane 0's chunk in the frame (chunk S of the warp starts 96*S bytes later)
+            const uint32_t wcoff = (uint32_t)((((uint64_t)s * G + b) * p.cps + bw * 32) * kChunkBytes);
+            wait_bar(bar_fdone + 8 * st, (ph_f >> st) & 1u);
+            ph_f ^= 1u << st;
+            uint32_t m[kMaskWords], cnt;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(cnt)
+                         : "r"(msk_addr + st * msk_stride + 16 * ftid)
+                         : "memory");
+            uint32_t wexc, total;
+            {
+                const uint32_t v = lane < (uint32_t)kWsFrontWarps ? wtot[st * 16 + lane] : 0u;
+                total = warp_add(v);
+                wexc = warp_add(lane < bw ? v : 0u);
+            }
+            if (scan_warp) {
+                // ---- cross-block exchange of the step: publish the block total, sum the predecessors (each lane reads
+                //      up to kWsLook descriptors, all in flight together: one L2 round trip)
+                unsigned long long *row = p.desc + (size_t)q * (G + 1);
+                if (lane == 0) desc_publish(row + b, ((unsigned long long)p.epoch << 32) | total);
+                unsigned long long pv[kWsLook], pv2 = 0;
+                const bool has2 = !REFREG && s > 0 && lane == 31;
+#pragma unroll
+                for (int i = 0; i < kWsLook; i++) {
+                    pv[i] = 0;
+                    if (lane + 32 * i < b) pv[i] = desc_peek(row + lane + 32 * i);
+                }
+                if (has2) pv2 = desc_peek(row - 1); // running total of the earlier segments: slot G of the previous step
+                auto settle = [&](unsigned long long v, const unsigned long long *d) -> uint32_t {
+                    uint32_t polls = 0;
+                    while ((uint32_t)(v >> 32) != p.epoch && !tripped) {
+                        __nanosleep(32);
+                        v = desc_peek(d);
+                        if (++polls > kWatchdogPolls) {
+                            tripped = true;
+                            atomicOr(p.status, kStatusWatchdog);
+                        }
+                    }
+                    return (uint32_t)v;
+                };
+                uint32_t part = 0;
+#pragma unroll
+                for (int i = 0; i < kWsLook; i++)
+                    if (lane + 32 * i < b) part += settle(pv[i], row + lane + 32 * i);
+                if (has2) part += settle(pv2, row - 1);
+                const uint32_t base = warp_add(part);
+                if (lane == 0) {
+                    sbase[st] = base;
+                    if (b == G - 1) {
+                        if (!REFREG) desc_publish(row + G, ((unsigned long long)p.epoch << 32) | (base + total));
+                        if (REFREG || s == p.nseg - 1) p.pos[t] = base + total;
+                    }
+                    if ((size_t)base + total > p.cap) atomicOr(p.status, kStatusCapacity);
+                    mbar_arrive(bar_base + 8 * st);
+                }
+            }
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t wrank = incl - cnt;
+            if (wtotal) {
+                wait_bar(bar_base + 8 * st, (ph_b >> st) & 1u);
+                const uint32_t base = *reinterpret_cast<volatile uint32_t *>(sbase + st);
+                int *xs_out = p.xs + (size_t)t * p.cap;
+                uint8_t *df_out = p.diff + (size_t)t * p.cap;
+                asm volatile("" : "+l"(xs_out), "+l"(df_out)); // keep the frame offset out of the emission loops
+                const size_t g0 = (size_t)base + wexc;
+                const uint32_t dv0 = stage_addr + st * stage_bytes + bw * 32 * kChunkBytes; // parked bytes of lane 0's chunk
+                if (wtotal <= (uint32_t)kWarpEntries) {
+                    uint32_t o = wrank + (uint32_t)(g0 & 3);
+#pragma unroll
+                    for (int w = 0; w < kMaskWords; w++)
+                        emit_bits(m[w], 32 * w, lane * kChunkBytes, dv0 + lane * kChunkBytes, sxs, sd, o);
+                    __syncwarp();
+                    flush_warp(sxs, sd, wcoff, xs_out, df_out, g0, wtotal, p.cap, lane);
+                } else if (g0 + wtotal <= (size_t)cap32) {
+                    emit_coop<false>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
+                } else {
+                    emit_coop<true>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
+                }
+            }
+            ph_b ^= 1u << st; // every step completes bar_base[st] exactly once, waited for or not
+            // ---- this warp is done with the stage; the last one refills it
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&done[st], 1u) == (uint32_t)kWsBackWarps - 1u) {
+                    done[st] = 0;
+                    if (q + nstages < nsteps) issue(q + nstages, st);
+                }
+            }
+            if (REFREG) ++t;
+            else if (++s == p.nseg) { s = 0; ++t; }
+            if (++st == nstages) st = 0;
+        }
+    }
+}
+
+} // namespace cvs

@@ -191,6 +191,44 @@ cvs_status cvs_noise_filter_device(const uint8_t *d_frame, uint8_t *d_out, int w
 cvs_status cvs_client_apply_device(uint8_t *d_frame, const int *d_xs, const uint8_t *d_diff,
                                    const unsigned int *d_pos, size_t capacity, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Opt-in compact wire format "CVW1" (SURVEY.md section 8f row 3).  The reference transmits, per frame, u32 pos,
+ * i32 xs[pos], u8 diff[pos] (server/src/threads.cpp:229-231; read back by client/opencv.cpp:52-66): 5 bytes per
+ * entry.  xs is ascending, so the index can travel as (tile, offset-in-tile) with tiles of CVS_WIRE_TILE bytes:
+ *     u32 magic "CVW1", u32 pos, u32 ntiles, u32 tile      16-byte header (little endian)
+ *     u8  count[ntiles]   padded to a multiple of 16       entries per tile (0..192)
+ *     u8  off[pos]        padded to a multiple of 16       offset of entry i inside its tile
+ *     u8  diff[pos]                                        value bytes, exactly the reference's
+ * = 16 + N/192 + 2*pos bytes instead of 4 + 5*pos (1080p: 157 KB instead of 311 KB at 1 % density, 1.28 MB instead of
+ * 3.11 MB at 10 %, 6.3 MB instead of 15.6 MB at 50 %).  The default everywhere stays the reference's format; a server
+ * and a client have to opt in together.
+ * --------------------------------------------------------------------------------------------------------------- */
+#define CVS_WIRE_TILE 192
+#define CVS_WIRE_MAGIC 0x31575643u
+/* largest encoded frame for this geometry: size wire_out buffers with it */
+size_t cvs_wire_bound(int width, int height);
+/* total bytes of an encoded frame, read from its header (host memory); 0 if the header is not CVW1 */
+size_t cvs_wire_size(const uint8_t *wire);
+/* cvs_submit_io that delivers the frame's payload as one CVW1 frame in wire_out (capacity cvs_wire_bound; pinned
+ * memory from cvs_alloc_host lets the device store it directly).  Complete it with cvs_wait(ticket); the count is
+ * the header's pos field. */
+cvs_status cvs_submit_wire(cvs_handle h, const uint8_t *frame, uint8_t *wire_out, uint8_t *show,
+                           const char *text, uint64_t *ticket);
+/* device-resident payload (as cvs_run_sequence_device leaves it for one frame) -> CVW1 frame in d_wire.
+ * d_scratch: (ntiles + 2) 32-bit words, ntiles = ceil(3*width*height / CVS_WIRE_TILE). */
+cvs_status cvs_wire_encode_device(const int *d_xs, const uint8_t *d_diff, const unsigned int *d_pos,
+                                  size_t capacity, int width, int height, uint32_t *d_scratch,
+                                  uint8_t *d_wire, void *cuda_stream);
+/* client side: decodes one CVW1 frame that lies in device memory.  Any of the outputs may be NULL:
+ *   d_frame : frame[x] += diff for every entry (client/opencv.cpp:64-66)
+ *   d_xs, d_diff, d_pos : the reference-format payload back (ascending indices)
+ * d_scratch as above.  An inconsistent frame (bad magic, other geometry, counts that do not add up to pos) is not
+ * applied at all; cvs_wire_decode_status (synchronises the stream) reports it. */
+cvs_status cvs_wire_decode_device(const uint8_t *d_wire, uint32_t *d_scratch, uint8_t *d_frame, int *d_xs,
+                                  uint8_t *d_diff, unsigned int *d_pos, int width, int height,
+                                  void *cuda_stream);
+cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int height, void *cuda_stream);
+
 /* Synthetic camera used by bench.py and the parity tests: counter-based
  * splitmix64 so that the numpy twin in cudavideostream_b200/synth.py produces identical bytes.
  *   cvs_synth_base_device   : base frame (diagonal gradient + noise)

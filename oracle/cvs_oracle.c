@@ -12,9 +12,13 @@
  *   K2  3x3 mean filter on the report's matrices A and B     (REPORT/report.tex:2351-2378)
  *   K4  histogram example                                    (REPORT/report.tex:3141-3187)
  *   K6  red byte of a changed byte index: i + (2 - i%3)      (REPORT/report.tex:2234)
- * The ordered (xs, diff) payload has no golden vector anywhere in the reference, so it is
- * pinned by this restatement of tests/cuda_streaming/test.cu:560-576 plus the client
- * round-trip property (client/opencv.cpp:64-66).
+ * and, since round 2, against the reference's own code run here (oracle/build_ref.py -> oracle/_ref/,
+ * tests/test_reference_server.py): the unmodified server/src/server.cpp built with -DCPU pins
+ * A3/A5/A6/A7 (gray average, histogram, two-max, binarize; server.cpp:96-135), and the unmodified
+ * server/src/kernels.cu run on the B200 pins A1 set-wise (same count, same (index, value) pairs).
+ * The ORDER of the (xs, diff) payload has no golden vector anywhere in the reference (kernel2's order
+ * is whatever atomicInc gave), so it is pinned by this restatement of tests/cuda_streaming/
+ * test.cu:560-576 plus the client round-trip property (client/opencv.cpp:64-66).
  *
  * Each function cites the reference file:line it follows (paths relative to the reference
  * root).  Floating point is kept in the reference's types and evaluation order; build with
@@ -475,4 +479,54 @@ ORC_API double orc_bench_diff_compact(const uint8_t *frames, int nframes_ring, i
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (sum_pos_out) *sum_pos_out = sum;
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---------------------------------------------------------------------------------------
+ * Synthetic camera: C twin of cudavideostream_b200/synth.py and of the device
+ * generator (csrc/cvs_filter_kernels.cuh k_synth_base / k_synth_next), so that bench.py's CPU legs can
+ * walk the very frames the GPU arm is timed on.  Not reference code: test infrastructure of this repo.
+ * ------------------------------------------------------------------------------------- */
+static uint64_t orc_splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+ORC_API void orc_synth_base(uint8_t *out, int width, int height, uint64_t seed)
+{
+    const uint32_t n = 3u * (uint32_t)width * (uint32_t)height;
+    const uint32_t den = (uint32_t)(width + height - 2);
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t px = i / 3u, ch = i - 3u * px;
+        const uint32_t x = px % (uint32_t)width, y = px / (uint32_t)width;
+        const int grad = den ? (int)(((x + y) * 255u) / den) : 0;
+        const uint64_t h = orc_splitmix64(seed + (uint64_t)i);
+        int v = grad + (int)(h & 63u) - 32 + 3 * (int)ch;
+        out[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+
+ORC_API void orc_synth_next(const uint8_t *prev, uint8_t *out, int total, uint64_t seed, uint32_t frame_index,
+                            uint32_t density_ppm)
+{
+    const uint64_t key = orc_splitmix64(seed ^ ((uint64_t)(frame_index + 1) * 0xD6E8FEB86659FD93ull));
+    for (int i = 0; i < total; i++) {
+        const uint64_t h = orc_splitmix64(key + (uint64_t)i);
+        const uint32_t u = (uint32_t)(h & 0xFFFFFu);
+        const int p = prev[i];
+        int v;
+        if ((((uint64_t)u * 1000000ull) >> 20) < (uint64_t)density_ppm) {
+            const int delta = 21 + (int)((h >> 20) % 60u);
+            v = ((h >> 40) & 1u) ? p + delta : p - delta;
+            if (v > 255) v = p - delta;
+            if (v < 0) v = p + delta;
+        } else {
+            v = p + (int)((h >> 24) % 7u) - 3;
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+        out[i] = (uint8_t)v;
+    }
 }

@@ -59,6 +59,8 @@ def _load(name: str = "liboracle.so") -> C.CDLL:
     lib.orc_reference.restype = _u8p
     lib.orc_reference.argtypes = [C.c_void_p]
     lib.orc_exec_core.argtypes = [C.c_void_p, _u8p, _u8p, C.c_char_p, C.POINTER(C.c_uint), _i32p]
+    lib.orc_synth_base.argtypes = [_u8p, C.c_int, C.c_int, C.c_uint64]
+    lib.orc_synth_next.argtypes = [_u8p, _u8p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32]
     lib.orc_bench_diff_compact.restype = C.c_double
     lib.orc_bench_diff_compact.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, C.c_int,
                                            C.POINTER(C.c_ulonglong)]
@@ -280,3 +282,16 @@ def bench_diff_compact(frames: np.ndarray, base: np.ndarray, thr: int, iters_per
     sec = L.orc_bench_diff_compact(_p8(frames.reshape(-1)), nring, total, thr, _p8(base),
                                    iters_per_thread, nthreads, C.byref(s))
     return sec, iters_per_thread * nthreads, s.value
+
+
+def synth_sequence(width: int, height: int, nframes: int, density_ppm: int, seed: int):
+    """C twin of cudavideostream_b200.synth.sequence (fast enough for full-size frames).  Returns (base, frames)."""
+    n = 3 * width * height
+    base = np.empty(n, dtype=np.uint8)
+    lib().orc_synth_base(_p8(base), width, height, seed & 0xFFFFFFFFFFFFFFFF)
+    frames = np.empty((nframes, n), dtype=np.uint8)
+    prev = base
+    for t in range(nframes):
+        lib().orc_synth_next(_p8(prev), _p8(frames[t]), n, seed & 0xFFFFFFFFFFFFFFFF, t, density_ppm)
+        prev = frames[t]
+    return base, frames
