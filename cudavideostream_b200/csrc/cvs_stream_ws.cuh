@@ -38,6 +38,12 @@ constexpr int kWsLook = 5;                                      // descriptors a
 #ifndef CVS_WS_BACK_REGS
 #define CVS_WS_BACK_REGS 48
 #endif
+// binarisation histogram (modes 5, 7): copies in shared memory, lane L adds to copy L mod kWsHistCopies, which cuts the
+// same-address serialisation of the shared atomics inside a warp (neighbouring pixels have similar gray values)
+#ifndef CVS_WS_HIST_COPIES
+#define CVS_WS_HIST_COPIES 4
+#endif
+constexpr int kWsHistCopies = CVS_WS_HIST_COPIES;
 static_assert(kWsFrontThreads == kThreads, "front threads own one chunk each, like k_stream's threads");
 static_assert(512 * CVS_WS_FRONT_REGS + 512 * CVS_WS_BACK_REGS <= 65536, "register file");
 
@@ -45,8 +51,9 @@ static_assert(512 * CVS_WS_FRONT_REGS + 512 * CVS_WS_BACK_REGS <= 65536, "regist
 // launch (cps), so four stages fit next to the mask queue at 1080p / 3840x2160 (cps = 438).
 struct WsLayout {
     static constexpr int lut = 0;                                      // 768 words
-    static constexpr int hist = lut + 768 * 4;                         // 256 words
-    static constexpr int bar_full = hist + 256 * 4;                    // kStages mbarriers: bulk copy landed
+    static constexpr int hist = 0;                                     // kWsHistCopies x 256 words, copy-interleaved; shares
+                                                                       // the table's bytes (a launch is heat map OR binarise)
+    static constexpr int bar_full = 4096;                              // kStages mbarriers: bulk copy landed
     static constexpr int bar_fdone = bar_full + 8 * 8;                 // kStages mbarriers: front warps done with the step
     static constexpr int bar_base = bar_fdone + 8 * 8;                 // kStages mbarriers: global offset of the block known
     static constexpr int done = bar_base + 8 * 8;                      // kStages words: back warps finished with the stage
@@ -56,13 +63,18 @@ struct WsLayout {
     static constexpr int sd = sxs + kWsBackWarps * SmemLayout::kXsHalves * 2;
     static constexpr int msk = (sd + kWsBackWarps * SmemLayout::kSdBytes + 127) / 128 * 128; // nstages * msk_stride
     static __host__ __device__ constexpr uint32_t msk_stride(uint32_t cps) { return (cps + 31u) / 32u * 32u * 16u; }
-    static __host__ __device__ constexpr uint32_t stage_bytes(uint32_t cps) { return (cps * kChunkBytes + 127u) / 128u * 128u; }
+    // whole warps of chunks: the dense emission walks all 32 chunks of a warp, also those past the block's slice
+    static __host__ __device__ constexpr uint32_t stage_bytes(uint32_t cps)
+    {
+        return ((cps + 31u) / 32u * 32u * kChunkBytes + 127u) / 128u * 128u;
+    }
     static __host__ __device__ constexpr uint32_t stage0(uint32_t cps, uint32_t nstages) { return msk + nstages * msk_stride(cps); }
     static __host__ __device__ constexpr uint32_t total(uint32_t cps, uint32_t nstages)
     {
         return stage0(cps, nstages) + nstages * stage_bytes(cps);
     }
 };
+static_assert(kWsHistCopies * 256 * 4 <= WsLayout::bar_full && 768 * 4 <= WsLayout::bar_full, "table / histogram region");
 static_assert(WsLayout::bar_full % 8 == 0 && WsLayout::sxs % 16 == 0 && WsLayout::sd % 16 == 0, "alignment");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
     const uint32_t nstages = p.nstages;
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t msk_stride = WsLayout::msk_stride(p.cps), stage_bytes = WsLayout::stage_bytes(p.cps);
+    const uint32_t nact = msk_stride / 16u; // front threads whose warp holds chunks (cps rounded up to whole warps)
     const uint32_t stage_addr = smem0 + WsLayout::stage0(p.cps, nstages);
     const uint32_t msk_addr = smem0 + WsLayout::msk;
     const uint32_t bar_full = smem0 + WsLayout::bar_full, bar_fdone = smem0 + WsLayout::bar_fdone,
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
     }
     if (kBinarize) {
         uint32_t *shist = reinterpret_cast<uint32_t *>(smem + WsLayout::hist);
-        for (uint32_t i = tid; i < 256; i += kWsThreads) shist[i] = 0;
+        for (uint32_t i = tid; i < 256 * kWsHistCopies; i += kWsThreads) shist[i] = 0;
     }
     __syncthreads();
     if (tid == 0)
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                             if ((uint32_t)px < npx) {
                                 uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
                                 if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
-                                atomicAdd(&shist[gv], 1u); // server.cpp:103-106
+                                atomicAdd(&shist[gv * kWsHistCopies + (lane & (kWsHistCopies - 1))], 1u); // server.cpp:103-106
                             }
                         }
                     }
@@ -319,18 +332,23 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
             }
             const uint32_t cnt = (uint32_t)__popc(m[0]) + (uint32_t)__popc(m[1]) + (uint32_t)__popc(m[2]);
             // hand the step to the back warps: (mask, count) per chunk, entries of this warp
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(msk_addr + st * msk_stride + 16 * tid), "r"(m[0]), "r"(m[1]),
-                         "r"(m[2]), "r"(cnt)
-                         : "memory");
+            if (tid < nact)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(msk_addr + st * msk_stride + 16 * tid), "r"(m[0]),
+                             "r"(m[1]), "r"(m[2]), "r"(cnt)
+                             : "memory");
             const uint32_t wsum = warp_add(cnt);
             if (lane == 0) wtot[st * 16 + warp] = wsum;
             if (kBinarize && s == p.nseg - 1) {
                 // histogram of the frame complete: flush and clear (front warps only: named barrier 1)
                 asm volatile("bar.sync 1, %0;" ::"n"(kWsFrontThreads) : "memory");
                 for (uint32_t i = tid; i < 256; i += kWsFrontThreads) {
-                    const uint32_t hv = shist[i];
+                    uint32_t hv = 0;
+#pragma unroll
+                    for (int c = 0; c < kWsHistCopies; c++) {
+                        hv += shist[i * kWsHistCopies + c];
+                        shist[i * kWsHistCopies + c] = 0;
+                    }
                     if (hv) atomicAdd(p.hist + (size_t)t * 256 + i, hv);
-                    shist[i] = 0;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kWsFrontThreads) : "memory");
             }
@@ -359,11 +377,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
             const uint32_t wcoff = (uint32_t)((((uint64_t)s * G + b) * p.cps + bw * 32) * kChunkBytes);
             wait_bar(bar_fdone + 8 * st, (ph_f >> st) & 1u);
             ph_f ^= 1u << st;
-            uint32_t m[kMaskWords], cnt;
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(cnt)
-                         : "r"(msk_addr + st * msk_stride + 16 * ftid)
-                         : "memory");
+            uint32_t m[kMaskWords] = {0, 0, 0}, cnt = 0;
+            if (ftid < nact)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(cnt)
+                             : "r"(msk_addr + st * msk_stride + 16 * ftid)
+                             : "memory");
             uint32_t wexc, total;
             {
                 const uint32_t v = lane < (uint32_t)kWsFrontWarps ? wtot[st * 16 + lane] : 0u;
