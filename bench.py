@@ -459,7 +459,7 @@ def side_workloads(cvs, torch, args, seqs, dev, local, rank, world, st, peak, ba
     # ---- config 5: eight independent 3840x2160 streams, stream sid on rank sid mod world
     mine = cvs.sharding.my_streams(C5_STREAMS, rank, world)
     T5 = C5_FRAMES
-    cap5 = N4K // 4
+    cap5 = N4K  # a re-run starts from the reference the previous run left behind: its first frame is dense
     pos5 = torch.zeros(T5, dtype=torch.int32, device=dev)
     xs5 = xs[:T5 * cap5] if xs.numel() >= T5 * cap5 else torch.empty(T5 * cap5, dtype=torch.int32, device=dev)
     df5 = df[:T5 * cap5] if df.numel() >= T5 * cap5 else torch.empty(T5 * cap5, dtype=torch.uint8, device=dev)
@@ -521,23 +521,33 @@ def e2e_run(cvs, torch, args, seqs, local, barrier):
         rings.append({"hb": hb, "stream": s, "out": out, "pending": [], "base": base})
     order = list(range(R)) + list(range(R - 2, 0, -1))
 
-    def run(nframes):
+    def run(nframes, wire=False):
+        """wire: the opt-in compact CVW1 frame (cvs_submit_wire) instead of the reference's (pos, xs, diff)."""
         d2h = 0
+
+        def account(pp, xb):
+            if wire:  # the encoded frame lies in xb (the slot's largest pinned buffer); its header holds the size
+                return int(cvs.wire.size_of(xb.array()[:16]))
+            return 4 + 5 * pp[0]
+
         for i in range(nframes):
             for q in rings:
                 s, hb, out, pending = q["stream"], q["hb"], q["out"], q["pending"]
                 fb, xb, pb = out[i % 4]
                 if len(pending) == 4:
-                    tk, pp = pending.pop(0)
+                    tk, pp, oxb = pending.pop(0)
                     s.wait(tk)
-                    d2h += 4 + 5 * pp[0]
+                    d2h += account(pp, oxb)
                 # frames stay in the pinned capture ring; the payload bytes go to the slot's own pinned buffer
                 src = order[i % len(order)]
-                pending.append((s.submit_io_raw(hb.ptr + src * N, fb.ptr, None, "", C.addressof(pb), xb.ptr), pb))
+                if wire:
+                    pending.append((s.submit_wire_raw(hb.ptr + src * N, xb.ptr, None, ""), pb, xb))
+                else:
+                    pending.append((s.submit_io_raw(hb.ptr + src * N, fb.ptr, None, "", C.addressof(pb), xb.ptr), pb, xb))
         for q in rings:
-            for tk, pp in q["pending"]:
+            for tk, pp, oxb in q["pending"]:
                 q["stream"].wait(tk)
-                d2h += 4 + 5 * pp[0]
+                d2h += account(pp, oxb)
             q["pending"].clear()
         return d2h
 
@@ -555,6 +565,20 @@ def e2e_run(cvs, torch, args, seqs, local, barrier):
            "frames": nfr, "seconds": dt, "gpu_launches": launches,
            "note": "one e2e step = %d frames per density x 3 densities per GPU through cvs_submit_io/cvs_wait from a "
                    "pinned host ring, the three streams submitted round-robin" % frames_per_density}
+
+    # ---- the same loop with the opt-in compact wire format (5 -> ~2 bytes per entry over PCIe)
+    for q in rings:
+        q["stream"].reset(q["base"])
+    run(min(8, frames_per_density), wire=True)
+    barrier()
+    t0 = time.perf_counter()
+    d2h_w = run(frames_per_density, wire=True)
+    torch.cuda.synchronize()
+    dt_w = time.perf_counter() - t0
+    dt_w, (nfr_w, d2h_w) = cvs.sharding.reduce_job(dt_w, [frames_per_density * len(rings), d2h_w], torch.device("cuda", local))
+    res["wire_cvw1"] = {"value": nfr_w / dt_w, "unit": "frames/s", "d2h_bytes_per_step": d2h_w,
+                        "note": "same frames through cvs_submit_wire: per-tile counts + one-byte offsets + values "
+                                "(include/cvs_b200.h), opt-in; the default stays the reference's format"}
 
     # ---- the synchronous drop-in call (cvs_exec: what the unchanged server.cpp:139 does), one stream at a time
     nsync = min(args.sync_frames, frames_per_density)

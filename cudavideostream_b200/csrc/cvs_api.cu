@@ -208,6 +208,7 @@ struct cvs_stream_s {
     cudaEvent_t ev_base = nullptr;
     bool push_payload = true; // CVS_PAYLOAD_PUSH=0 falls back to count round trip + copy engine
     bool speculate = true;    // CVS_EGRESS_SPECULATE=0: cvs_submit_io never copies a predicted payload size
+    bool speculate_all = false; // CVS_EGRESS_SPECULATE=2: ... and 2: also for payloads above N/4 entries (measurements)
     uint32_t pred = 0;        // predicted entries of the next frame (previous count + margin)
     cvs::ConvWeights weights;
     int sms = 0;
@@ -222,6 +223,8 @@ struct cvs_stream_s {
     unsigned int *h_status = nullptr; // pinned
     unsigned long long *d_desc = nullptr;
     size_t desc_words = 0;
+    unsigned int *d_band_pos = nullptr; // banded launches: two arrays of per-frame counts so far (ping-pong)
+    size_t band_frames = 0;
     uint32_t epoch = 0;
     // scratch that grows with the longest sequence seen
     uint8_t *d_work = nullptr;   // filtered / overlaid frames
@@ -237,6 +240,7 @@ struct cvs_stream_s {
     int occ_cache[8][2][2] = {}; // co-resident blocks per SM of each k_stream variant (0 = not queried yet)
     int occ_ws[8][2][2] = {};    // same for k_stream_ws
     bool use_ws = true;          // CVS_STREAM_KERNEL=v1 selects the one-group kernel (k_stream) for A/B measurements
+    bool force_ws = false;       // CVS_STREAM_KERNEL=ws: k_stream_ws also for multi-pass frames
     uint64_t next_ticket = 1;
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
@@ -391,14 +395,34 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 
     // ---- geometry of the persistent launch: G co-resident blocks, each owning the same cps consecutive chunks of
     //      every frame; frames larger than G * 512 chunks take nseg passes
-    const bool ws = h->use_ws;
+    // k_stream_ws (front / back warp groups) where the reference stays in registers; frames that take several passes
+    // of the grid (3840x2160) keep the one-group kernel, which measured faster there (17 vs 25 us per frame at 1 %)
+    // Frames that do not fit one pass of the grid (3840x2160): a SEQUENCE is walked band by band -- every band is a
+    // byte range of the frame that does fit, and one k_stream_ws launch takes that band through all frames of the
+    // piece with its reference bytes in registers; frame t's entries of band j are appended behind those of the bands
+    // before it (counts handed from launch to launch).  Same payload, 1.9x faster than walking the frame in
+    // segments with the reference going through L2.  Single frames (the drop-in call) keep the one-launch kernel.
+    bool ws = h->use_ws;
+    int nbands = 1;
+    {
+        const int g0 = h->sms < 32 * cvs::kWsLook ? h->sms : 32 * cvs::kWsLook;
+        if (ws && h->nchunks > (size_t)g0 * cvs::kThreads) {
+            if (piece_max >= 4 && !h->force_ws)
+                nbands = (int)((h->nchunks + (size_t)g0 * cvs::kThreads - 1) / ((size_t)g0 * cvs::kThreads));
+            else if (!h->force_ws)
+                ws = false; // k_stream (segments, reference through L2)
+        }
+    }
+    const size_t band_chunks_total = (h->nchunks + nbands - 1) / nbands; // chunks per band before rounding to the grid
+    const uint32_t geo_chunks = nbands > 1 ? (uint32_t)band_chunks_total : h->nchunks;
     int G = ws ? h->sms : cvs::kBlocksPerSM * h->sms;
     const int look_max = ws ? 32 * cvs::kWsLook : cvs::kLook * cvs::kThreads; // predecessors the look-back can read
     if (G > look_max) G = look_max;
-    if ((uint32_t)G > h->nchunks) G = (int)h->nchunks;
-    uint32_t nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
-    uint32_t cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+    if ((uint32_t)G > geo_chunks) G = (int)geo_chunks;
+    uint32_t nseg = (uint32_t)((geo_chunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+    uint32_t cps = (uint32_t)((geo_chunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
     const bool refreg = nseg == 1;
+    if (nbands > 1 && !refreg) return fail(CVS_ERR_INTERNAL, "band geometry does not fit one pass");
     StreamKernel kern = ws ? pick_ws_kernel(kmode, h->hi, refreg) : pick_kernel(kmode, h->hi, refreg);
     const int block_threads = ws ? cvs::kWsThreads : cvs::kThreads;
     // ring depth: all four stages when the reference lives in registers (measured +5 % at 1080p), three when it goes
@@ -421,9 +445,19 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     if (occ < 1) return fail(CVS_ERR_INTERNAL, "stream kernel does not fit on an SM");
     if (G > occ * h->sms) { // fewer co-resident blocks than planned: recompute
         G = occ * h->sms;
-        nseg = (uint32_t)((h->nchunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
-        cps = (uint32_t)((h->nchunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
+        nseg = (uint32_t)((geo_chunks + (size_t)G * cvs::kThreads - 1) / ((size_t)G * cvs::kThreads));
+        cps = (uint32_t)((geo_chunks + (size_t)G * nseg - 1) / ((size_t)G * nseg));
         if ((nseg == 1) != refreg) return fail(CVS_ERR_INTERNAL, "occupancy changed the segment count");
+    }
+    if (nbands > 1 && h->band_frames < (size_t)piece_max) {
+        if (h->d_band_pos) {
+            CU_TRY(cudaDeviceSynchronize());
+            cudaFree(h->d_band_pos);
+            h->d_band_pos = nullptr;
+            h->band_frames = 0;
+        }
+        CU_TRY(cudaMalloc(&h->d_band_pos, 2 * (size_t)piece_max * sizeof(unsigned int)));
+        h->band_frames = (size_t)piece_max;
     }
 
     int done = 0;
@@ -458,40 +492,49 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 
         cvs_status s = ensure_desc(h, (size_t)piece * nseg * (G + 1));
         if (s) return s;
-        h->epoch++;
-        if (h->epoch == 0) { // tag wrapped: stale descriptors could alias
-            CU_TRY(cudaMemsetAsync(h->d_desc, 0, h->desc_words * sizeof(unsigned long long), st));
-            h->epoch = 1;
+        const size_t band_bytes = (size_t)G * cps * cvs::kChunkBytes; // bytes of a band (the last one may be shorter)
+        for (int band = 0; band < nbands; band++) {
+            const size_t boff = nbands > 1 ? (size_t)band * band_bytes : 0;
+            if (boff >= h->N) break;
+            const uint32_t bbytes = nbands > 1 ? (uint32_t)((h->N - boff) < band_bytes ? (h->N - boff) : band_bytes) : h->N;
+            h->epoch++;
+            if (h->epoch == 0) { // tag wrapped: stale descriptors could alias
+                CU_TRY(cudaMemsetAsync(h->d_desc, 0, h->desc_words * sizeof(unsigned long long), st));
+                h->epoch = 1;
+            }
+            const bool last_band = nbands == 1 || boff + band_bytes >= h->N;
+            cvs::StreamParams p;
+            p.frames = frames + boff;
+            p.frame_stride = fstride;
+            p.nframes = piece;
+            p.ref = h->d_ref + boff;
+            p.nbytes = bbytes;
+            p.nbytes16 = nbands > 1 ? (uint32_t)round_up(bbytes, 16) : h->N16;
+            p.nchunks = (bbytes + cvs::kChunkBytes - 1) / cvs::kChunkBytes;
+            p.nseg = nseg;
+            p.cps = cps;
+            p.nstages = (uint32_t)nstages;
+            p.pos = last_band ? d_pos + done : h->d_band_pos + (size_t)(band & 1) * h->band_frames;
+            p.pos_prior = band ? h->d_band_pos + (size_t)((band - 1) & 1) * h->band_frames : nullptr;
+            p.index_base = (uint32_t)boff;
+            p.xs = d_xs + (size_t)done * cap;
+            p.diff = d_diff + (size_t)done * cap;
+            p.cap = cap;
+            p.show = d_show ? d_show + (size_t)done * show_stride : nullptr;
+            p.show_stride = show_stride;
+            p.gray1 = binarize ? h->d_gray1 : nullptr;
+            p.gray_stride = h->P16;
+            p.hist = binarize ? h->d_hist : nullptr;
+            p.heat_lut = h->d_lut;
+            p.desc = h->d_desc;
+            p.epoch = h->epoch;
+            p.addc = h->addc;
+            p.debug = h->debug;
+            p.status = d_status;
+            void *args[] = {&p};
+            CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
+            h->launches++;
         }
-        cvs::StreamParams p;
-        p.frames = frames;
-        p.frame_stride = fstride;
-        p.nframes = piece;
-        p.ref = h->d_ref;
-        p.nbytes = h->N;
-        p.nbytes16 = h->N16;
-        p.nchunks = h->nchunks;
-        p.nseg = nseg;
-        p.cps = cps;
-        p.nstages = (uint32_t)nstages;
-        p.pos = d_pos + done;
-        p.xs = d_xs + (size_t)done * cap;
-        p.diff = d_diff + (size_t)done * cap;
-        p.cap = cap;
-        p.show = d_show ? d_show + (size_t)done * show_stride : nullptr;
-        p.show_stride = show_stride;
-        p.gray1 = binarize ? h->d_gray1 : nullptr;
-        p.gray_stride = h->P16;
-        p.hist = binarize ? h->d_hist : nullptr;
-        p.heat_lut = h->d_lut;
-        p.desc = h->d_desc;
-        p.epoch = h->epoch;
-        p.addc = h->addc;
-        p.debug = h->debug;
-        p.status = d_status;
-        void *args[] = {&p};
-        CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
-        h->launches++;
 
         if (binarize) {
             cvs::k_threshold<<<piece, 256, 0, st>>>(h->d_hist, h->d_thr, piece, 50, 200);
@@ -601,9 +644,15 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     if (const char *dbg = getenv("CVS_DEBUG_FLAGS")) h->debug = (uint32_t)atoi(dbg);
     if (const char *sg = getenv("CVS_STAGES")) h->stages = atoi(sg);
 #endif
-    if (const char *kk = getenv("CVS_STREAM_KERNEL")) h->use_ws = strcmp(kk, "v1") != 0; // both kernels are bit-exact
+    if (const char *kk = getenv("CVS_STREAM_KERNEL")) { // both kernels are bit-exact; the switch exists for A/B timing
+        h->use_ws = strcmp(kk, "v1") != 0;
+        h->force_ws = strcmp(kk, "ws") == 0;
+    }
     if (const char *pp = getenv("CVS_PAYLOAD_PUSH")) h->push_payload = atoi(pp) != 0;
-    if (const char *sp = getenv("CVS_EGRESS_SPECULATE")) h->speculate = atoi(sp) != 0;
+    if (const char *sp = getenv("CVS_EGRESS_SPECULATE")) {
+        h->speculate = atoi(sp) != 0;
+        h->speculate_all = atoi(sp) == 2;
+    }
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
@@ -666,8 +715,16 @@ cvs_status init_device_state(cvs_handle h, const cvs_config *cfg)
         cudaEvent_t *evs[] = {&s.ev_h2d0, &s.ev_h2d1, &s.ev_k0, &s.ev_k1, &s.ev_pos, &s.ev_p0, &s.ev_done};
         for (cudaEvent_t *e : evs) CU_TRY(cudaEventCreate(e));
     }
-    CU_TRY(cudaEventCreate(&h->ev_base));
-    CU_TRY(cudaEventRecord(h->ev_base, h->s_h2d));
+    {   // CVS_TRACE timelines of all handles of the process share one origin
+        static cudaEvent_t g_trace_base = nullptr;
+        static std::mutex g_trace_mutex;
+        std::lock_guard<std::mutex> lk(g_trace_mutex);
+        if (!g_trace_base) {
+            CU_TRY(cudaEventCreate(&g_trace_base));
+            CU_TRY(cudaEventRecord(g_trace_base, h->s_h2d));
+        }
+        h->ev_base = g_trace_base;
+    }
     CU_TRY(cudaDeviceSynchronize());
     return CVS_OK;
 }
@@ -693,9 +750,9 @@ cvs_status cvs_destroy(cvs_handle h)
             if (e) cudaEventDestroy(e);
     }
     cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
+    cudaFree(h->d_band_pos);
     cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
     cudaFree(h->d_glyphs);
-    if (h->ev_base) cudaEventDestroy(h->ev_base);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -773,8 +830,11 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     //     no SM time (the copy kernel of (b) delays the next frame's cooperative launch), and the D2H engine runs
     //     beside the next frame's H2D; cvs_wait fetches the remainder in the rare case the frame had more.  Bytes
     //     past *pos of diff_out / xs are unspecified on that entry point, so the over-copy is invisible.  Measured
-    //     (1080p, frames/s at 1 / 10 / 50 % density): 7,559 / 6,776 / 2,572 against 7,794 / 5,856 / 3,042 for (b):
-    //     small payloads do not repay the extra copy calls and large ones not the over-copy, hence the window.
+    //     (1080p, one stream, frames/s at 1 / 10 / 50 % density): 7,559 / 6,776 / 2,572 against 7,794 / 5,856 / 3,042
+    //     for (b): small payloads do not repay the extra copy calls and large ones not the over-copy, hence the
+    //     window.  (Round 2, three interleaved streams per GPU: taking the copy engine for the 50 % stream as well
+    //     measured 4,680 frames/s against 5,260 with the push -- the path is bound by the PCIe link's combined
+    //     traffic of both directions, about 62 GB/s on the pool's boxes, and the over-copy only adds to it.)
     // (b) otherwise, and always in-place (cvs_submit / cvs_exec: "rest of the frame untouched"): a copy kernel that
     //     reads the count on the device pushes exactly pos entries into the caller's pinned buffers, or (c) count
     //     round trip + exact copies in cvs_wait when the buffers are not mapped.
@@ -799,7 +859,8 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     // only with a prediction from a previous frame, and never more entries than the caller's buffers hold (N)
     if (wire_out) {
         // nothing else to fetch: the encoded frame carries the count
-    } else if (h->speculate && diff_out != frame && h->pred != 0 && h->pred >= spec_lo && h->pred <= h->N / 4u) {
+    } else if (h->speculate && diff_out != frame && h->pred != 0 && h->pred >= spec_lo &&
+               (h->pred <= h->N / 4u || h->speculate_all)) {
         const size_t guess = round_up(h->pred, 4);
         s.spec = (uint32_t)(guess > h->N ? h->N : guess);
     } else {
@@ -890,8 +951,9 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
         float t[6] = {0, 0, 0, 0, 0, 0};
         cudaEvent_t ev[6] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.copied ? s.ev_done : s.ev_pos};
         for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], h->ev_base, ev[i]);
-        fprintf(stderr, "ticket %llu h2d %.1f-%.1f kern %.1f-%.1f pos %.1f done %.1f us\n", (unsigned long long)ticket,
-                t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3);
+        fprintf(stderr, "stream %p ticket %llu h2d %.1f-%.1f kern %.1f-%.1f pos %.1f done %.1f us n %u %s\n", (void *)h,
+                (unsigned long long)ticket, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, n,
+                s.pushed ? "push" : (s.spec ? "spec" : "copy"));
     }
     return CVS_OK;
 }

@@ -101,6 +101,11 @@ struct StreamParams {
     uint32_t epoch;             // tag of this launch
     uint32_t addc;              // threshold constant for changed80<>
     unsigned int *status;       // StatusBits
+    // banded launches (k_stream_ws only; 0 / nullptr otherwise): the launch covers the byte range
+    // [index_base, index_base + nbytes) of larger frames -- frames, ref are already offset by the host; indices and
+    // display offsets get index_base added -- and frame t's entries follow the pos_prior[t] entries of the bands before
+    uint32_t index_base;
+    const unsigned int *pos_prior;
     uint32_t debug;             // profiling experiments only (CVS_DEBUG_FLAGS): 1 no look-back, 2 no emission, 4 no per-word pass
 };
 

@@ -38,10 +38,18 @@ constexpr int kWsLook = 5;                                      // descriptors a
 #ifndef CVS_WS_BACK_REGS
 #define CVS_WS_BACK_REGS 48
 #endif
+// pause between two probes of an mbarrier (ns): front warps waiting for their slice / back warps waiting for the front
+// or for the block's global offset
+#ifndef CVS_WS_SLEEP_FULL
+#define CVS_WS_SLEEP_FULL 100
+#endif
+#ifndef CVS_WS_SLEEP_BACK
+#define CVS_WS_SLEEP_BACK 200
+#endif
 // binarisation histogram (modes 5, 7): copies in shared memory, lane L adds to copy L mod kWsHistCopies, which cuts the
 // same-address serialisation of the shared atomics inside a warp (neighbouring pixels have similar gray values)
 #ifndef CVS_WS_HIST_COPIES
-#define CVS_WS_HIST_COPIES 4
+#define CVS_WS_HIST_COPIES 1   // 4 copies measured 2 % SLOWER (7.29 vs 7.16 us per frame, mode 5): the atomics are not conflict-bound
 #endif
 constexpr int kWsHistCopies = CVS_WS_HIST_COPIES;
 static_assert(kWsFrontThreads == kThreads, "front threads own one chunk each, like k_stream's threads");
@@ -55,10 +63,12 @@ struct WsLayout {
                                                                        // the table's bytes (a launch is heat map OR binarise)
     static constexpr int bar_full = 4096;                              // kStages mbarriers: bulk copy landed
     static constexpr int bar_fdone = bar_full + 8 * 8;                 // kStages mbarriers: front warps done with the step
-    static constexpr int bar_base = bar_fdone + 8 * 8;                 // kStages mbarriers: global offset of the block known
+    static constexpr int bar_base = bar_fdone + 8 * 8;                 // 2 x kStages mbarriers: global offset of the block known
     static constexpr int done = bar_base + 8 * 8;                      // kStages words: back warps finished with the stage
-    static constexpr int base = done + 8 * 4;                          // kStages words: global rank of the block's first entry
-    static constexpr int wtot = base + 8 * 4;                          // kStages x 16 words: entries per front warp
+    static constexpr int base = done + 8 * 4;                          // 2 x kStages words: global rank of the block's first entry
+    static constexpr int fcnt = base + 8 * 4;                          // kStages words: front warps that have posted their total
+    static constexpr int ftot = fcnt + 8 * 4;                          // kStages words: entries of the block in the step so far
+    static constexpr int wtot = ftot + 8 * 4;                          // kStages x 16 words: entries per front warp
     static constexpr int sxs = wtot + 8 * 16 * 4;                      // kWsBackWarps * kXsHalves uint16
     static constexpr int sd = sxs + kWsBackWarps * SmemLayout::kXsHalves * 2;
     static constexpr int msk = (sd + kWsBackWarps * SmemLayout::kSdBytes + 127) / 128 * 128; // nstages * msk_stride
@@ -75,11 +85,48 @@ struct WsLayout {
     }
 };
 static_assert(kWsHistCopies * 256 * 4 <= WsLayout::bar_full && 768 * 4 <= WsLayout::bar_full, "table / histogram region");
+static_assert(2 * kStages <= 8, "bar_base / base slots");
 static_assert(WsLayout::bar_full % 8 == 0 && WsLayout::sxs % 16 == 0 && WsLayout::sd % 16 == 0, "alignment");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Coalesced flush by one warp of n entries staged at elements [0, n) of its window, to global ranks g0 .. g0 + n - 1.
+// Unlike flush_warp (k_stream) the window was filled BEFORE g0 was known, so shared and global memory are not aligned
+// to each other: the 16-byte index vector / 4-byte value word of a quad is cut out of two aligned shared loads with a
+// funnel shift (the misalignment is the same for every quad of the warp).
+__device__ __forceinline__ void flush_warp_shifted(const uint16_t *sxs, const uint8_t *sd, uint32_t wbase, int *xs_out,
+                                                   uint8_t *df_out, size_t g0, uint32_t n, size_t cap, uint32_t lane)
+{
+    if (g0 >= cap) return;
+    if (g0 + n > cap) n = (uint32_t)(cap - g0);
+    const uint32_t a = (4u - (uint32_t)(g0 & 3)) & 3u; // elements in front of the first rank that is a multiple of 4
+    const uint32_t head = min(a, n);
+    const uint32_t nq = (n - head) >> 2;               // whole quads: elements head + 4k .. head + 4k + 3
+    int *xg = xs_out + g0;
+    uint8_t *dg = df_out + g0;
+    const uint32_t sx = smem_u32(sxs), sv = smem_u32(sd);
+    const uint32_t sh16 = 16u * (a & 1u), sh8 = 8u * a;
+#pragma unroll 1
+    for (uint32_t k = lane; k < nq; k += 32) {
+        uint32_t w0, w1, w2, w3, d0, d1;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(sx + 8 * k) : "memory");
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w2), "=r"(w3) : "r"(sx + 8 * k + 8) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d0) : "r"(sv + 4 * k) : "memory");
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d1) : "r"(sv + 4 * k + 4) : "memory");
+        if (a & 2u) { w0 = w1; w1 = w2; w2 = w3; }
+        const uint32_t x = __funnelshift_r(w0, w1, sh16), y = __funnelshift_r(w1, w2, sh16);
+        stg_stream(xg + head + 4 * k, make_uint4(wbase + (x & 0xffffu), wbase + (x >> 16), wbase + (y & 0xffffu), wbase + (y >> 16)));
+        stg_stream_u32(dg + head + 4 * k, __funnelshift_r(d0, d1, sh8));
+    }
+    // the (at most three + three) entries in front of the first and behind the last whole quad: one lane each
+    const uint32_t e1 = lane < 4 ? lane : head + 4 * nq + (lane - 4);
+    if (lane < 8 && e1 < (lane < 4 ? head : n)) {
+        stg_stream_u32(xg + e1, wbase + sxs[e1]);
+        stg_stream_u8(dg + e1, sd[e1]);
+    }
 }
 
 template <int MODE, bool HI, bool REFREG>
@@ -99,6 +146,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
     const uint32_t bar_full = smem0 + WsLayout::bar_full, bar_fdone = smem0 + WsLayout::bar_fdone,
                    bar_base = smem0 + WsLayout::bar_base;
     uint32_t *done = reinterpret_cast<uint32_t *>(smem + WsLayout::done);
+    uint32_t *fcnt = reinterpret_cast<uint32_t *>(smem + WsLayout::fcnt);
+    uint32_t *ftot = reinterpret_cast<uint32_t *>(smem + WsLayout::ftot);
     uint32_t *sbase = reinterpret_cast<uint32_t *>(smem + WsLayout::base);
     uint32_t *wtot = reinterpret_cast<uint32_t *>(smem + WsLayout::wtot);
     constexpr bool kBinarize = (MODE == kModeBinarize || MODE == kModeBinarizeAvg);
@@ -124,6 +173,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // parked bytes were written through the generic proxy
             mbar_expect_tx(bar_full + 8 * st, bytes);
             bulk_g2s(stage_addr + st * stage_bytes, p.frames + (size_t)t * p.frame_stride + off, bytes, bar_full + 8 * st, pol);
+        } else {
+            // a block whose slice lies past the end of the frame still hands the stage over: the front warps must not
+            // run ahead of the back warps by more than the ring (fdone[st] would complete twice before it is waited for)
+            mbar_arrive(bar_full + 8 * st);
         }
     };
 
@@ -133,7 +186,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_fdone + 8 * i, kWsFrontWarps);
             mbar_init(bar_base + 8 * i, 1);
+            mbar_init(bar_base + 8 * (i + kStages), 1);
             done[i] = 0;
+            fcnt[i] = 0;
+            ftot[i] = 0;
         }
         mbar_init_fence();
     }
@@ -152,8 +208,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
     // a spin wait that gave up once stops every later wait of the thread (the launch must terminate); the status word
     // tells the host
     bool tripped = false;
-    auto wait_bar = [&](uint32_t bar, uint32_t parity) {
-        if (!tripped && !mbar_wait(bar, parity)) {
+    auto wait_bar = [&](uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+        if (!tripped && !mbar_wait(bar, parity, sleep_ns)) {
             tripped = true;
             atomicOr(p.status, kStatusWatchdog);
         }
@@ -208,10 +264,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                 geometry(s);
                 load_ref(); // L2 hit; issued before the wait on the frame slice
             }
-            if (sbytes) {
-                wait_bar(bar_full + 8 * st, (phase >> st) & 1u);
-                phase ^= 1u << st;
-            }
+            wait_bar(bar_full + 8 * st, (phase >> st) & 1u, CVS_WS_SLEEP_FULL); // completes at once for an empty slice (see issue())
+            phase ^= 1u << st;
             const uint32_t myaddr = stage_addr + st * stage_bytes + tid * kChunkBytes;
             uint32_t m[kMaskWords] = {0, 0, 0};
             constexpr bool kStreamLoad = (MODE == kModeNone);
@@ -249,7 +303,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
 #pragma unroll
                 for (int g = 0; g < kGroupsPerThread; g++) {
                     const uint32_t gb = sw ? (uint32_t)(1 - g) * kGroupBytes : (uint32_t)g * kGroupBytes;
-                    const uint32_t goff = coff + gb;
+                    const uint32_t goff = p.index_base + coff + gb; // byte offset of the group in the whole frame
                     const uint32_t gnv = nv > gb ? min(nv - gb, (uint32_t)kGroupBytes) : 0u;
                     if (gnv == 0) continue;
                     uint32_t cg[kGroupWords], rg[kGroupWords], o[kGroupWords];
@@ -337,7 +391,19 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                              "r"(m[1]), "r"(m[2]), "r"(cnt)
                              : "memory");
             const uint32_t wsum = warp_add(cnt);
-            if (lane == 0) wtot[st * 16 + warp] = wsum;
+            if (lane == 0) {
+                wtot[st * 16 + warp] = wsum;
+                // the block total of the step goes out to the other blocks as early as possible: the last front warp to
+                // get here publishes it (the back warps' look-back then rarely has to wait for a predecessor)
+                atomicAdd(&ftot[st], wsum);
+                __threadfence_block();
+                if (atomicAdd(&fcnt[st], 1u) == (uint32_t)kWsFrontWarps - 1u) {
+                    __threadfence_block();
+                    const uint32_t total = atomicExch(&ftot[st], 0u);
+                    fcnt[st] = 0;
+                    desc_publish(p.desc + (size_t)q * (G + 1) + b, ((unsigned long long)p.epoch << 32) | total);
+                }
+            }
             if (kBinarize && s == p.nseg - 1) {
                 // histogram of the frame complete: flush and clear (front warps only: named barrier 1)
                 asm volatile("bar.sync 1, %0;" ::"n"(kWsFrontThreads) : "memory");
@@ -374,8 +440,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
         uint32_t ph_f = 0, ph_b = 0, st = 0, t = 0, s = 0;
         for (uint32_t q = 0; q < nsteps; q++) {
             // byte offset of lane 0's chunk in the frame (chunk S of the warp starts 96*S bytes later)
-            const uint32_t wcoff = (uint32_t)((((uint64_t)s * G + b) * p.cps + bw * 32) * kChunkBytes);
-            wait_bar(bar_fdone + 8 * st, (ph_f >> st) & 1u);
+            const uint32_t wcoff = p.index_base + (uint32_t)((((uint64_t)s * G + b) * p.cps + bw * 32) * kChunkBytes);
+            // global-offset slot of the step: 2 x nstages slots, because a sparse warp lets its stage go before it waits
+            // for the offset, so the look-back warp may be up to nstages steps ahead of it (not more: the bulk copy of
+            // step q + nstages + 1 needs this warp's release of step q + 1)
+            const uint32_t bslot = q & (2u * kStages - 1u);
+            wait_bar(bar_fdone + 8 * st, (ph_f >> st) & 1u, CVS_WS_SLEEP_BACK);
             ph_f ^= 1u << st;
             uint32_t m[kMaskWords] = {0, 0, 0}, cnt = 0;
             if (ftid < nact)
@@ -390,10 +460,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                 wexc = warp_add(lane < bw ? v : 0u);
             }
             if (scan_warp) {
-                // ---- cross-block exchange of the step: publish the block total, sum the predecessors (each lane reads
-                //      up to kWsLook descriptors, all in flight together: one L2 round trip)
-                unsigned long long *row = p.desc + (size_t)q * (G + 1);
-                if (lane == 0) desc_publish(row + b, ((unsigned long long)p.epoch << 32) | total);
+                // ---- cross-block exchange of the step: sum the predecessors' totals (each lane reads up to kWsLook
+                //      descriptors, all in flight together: one L2 round trip)
+                unsigned long long *row = p.desc + (size_t)q * (G + 1); // (the block's own total was published by the front)
                 unsigned long long pv[kWsLook], pv2 = 0;
                 const bool has2 = !REFREG && s > 0 && lane == 31;
 #pragma unroll
@@ -402,6 +471,8 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                     if (lane + 32 * i < b) pv[i] = desc_peek(row + lane + 32 * i);
                 }
                 if (has2) pv2 = desc_peek(row - 1); // running total of the earlier segments: slot G of the previous step
+                uint32_t prior = 0;                 // entries of the frame that earlier bands (launches) produced
+                if (p.pos_prior && lane == 0) prior = p.pos_prior[t];
                 auto settle = [&](unsigned long long v, const unsigned long long *d) -> uint32_t {
                     uint32_t polls = 0;
                     while ((uint32_t)(v >> 32) != p.epoch && !tripped) {
@@ -414,56 +485,68 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                     }
                     return (uint32_t)v;
                 };
-                uint32_t part = 0;
+                uint32_t part = prior;
 #pragma unroll
                 for (int i = 0; i < kWsLook; i++)
                     if (lane + 32 * i < b) part += settle(pv[i], row + lane + 32 * i);
                 if (has2) part += settle(pv2, row - 1);
                 const uint32_t base = warp_add(part);
                 if (lane == 0) {
-                    sbase[st] = base;
+                    sbase[bslot] = base;
                     if (b == G - 1) {
                         if (!REFREG) desc_publish(row + G, ((unsigned long long)p.epoch << 32) | (base + total));
                         if (REFREG || s == p.nseg - 1) p.pos[t] = base + total;
                     }
                     if ((size_t)base + total > p.cap) atomicOr(p.status, kStatusCapacity);
-                    mbar_arrive(bar_base + 8 * st);
+                    mbar_arrive(bar_base + 8 * bslot);
                 }
             }
             const uint32_t incl = warp_incl_scan(cnt, lane);
             const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
             const uint32_t wrank = incl - cnt;
+            const uint32_t dv0 = stage_addr + st * stage_bytes + bw * 32 * kChunkBytes; // parked bytes of lane 0's chunk
+            // this warp is done with the ring stage; the last warp to say so refills it
+            auto release_stage = [&]() {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&done[st], 1u) == (uint32_t)kWsBackWarps - 1u) {
+                        done[st] = 0;
+                        if (q + nstages < nsteps) issue(q + nstages, st);
+                    }
+                }
+            };
+            // A warp whose entries fit its window copies them out of the stage NOW, in rank order, and lets the stage
+            // go before it waits for the block's global offset: the look-back latency is then outside the stage's
+            // lifetime (bulk copy -> pass -> this copy), which is what bounds the step rate with four stages.
+            const bool sparse = wtotal <= (uint32_t)kWarpEntries;
+            if (sparse) {
+                if (wtotal) {
+                    uint32_t o = wrank;
+#pragma unroll
+                    for (int w = 0; w < kMaskWords; w++)
+                        emit_bits(m[w], 32 * w, lane * kChunkBytes, dv0 + lane * kChunkBytes, sxs, sd, o);
+                }
+                release_stage();
+            }
             if (wtotal) {
-                wait_bar(bar_base + 8 * st, (ph_b >> st) & 1u);
-                const uint32_t base = *reinterpret_cast<volatile uint32_t *>(sbase + st);
+                wait_bar(bar_base + 8 * bslot, (ph_b >> bslot) & 1u, CVS_WS_SLEEP_BACK);
+                const uint32_t base = *reinterpret_cast<volatile uint32_t *>(sbase + bslot);
                 int *xs_out = p.xs + (size_t)t * p.cap;
                 uint8_t *df_out = p.diff + (size_t)t * p.cap;
                 asm volatile("" : "+l"(xs_out), "+l"(df_out)); // keep the frame offset out of the emission loops
                 const size_t g0 = (size_t)base + wexc;
-                const uint32_t dv0 = stage_addr + st * stage_bytes + bw * 32 * kChunkBytes; // parked bytes of lane 0's chunk
-                if (wtotal <= (uint32_t)kWarpEntries) {
-                    uint32_t o = wrank + (uint32_t)(g0 & 3);
-#pragma unroll
-                    for (int w = 0; w < kMaskWords; w++)
-                        emit_bits(m[w], 32 * w, lane * kChunkBytes, dv0 + lane * kChunkBytes, sxs, sd, o);
-                    __syncwarp();
-                    flush_warp(sxs, sd, wcoff, xs_out, df_out, g0, wtotal, p.cap, lane);
+                if (sparse) {
+                    flush_warp_shifted(sxs, sd, wcoff, xs_out, df_out, g0, wtotal, p.cap, lane);
+                    __syncwarp(); // the window is refilled by the next step
                 } else if (g0 + wtotal <= (size_t)cap32) {
                     emit_coop<false>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
                 } else {
                     emit_coop<true>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
                 }
             }
-            ph_b ^= 1u << st; // every step completes bar_base[st] exactly once, waited for or not
-            // ---- this warp is done with the stage; the last one refills it
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                if (atomicAdd(&done[st], 1u) == (uint32_t)kWsBackWarps - 1u) {
-                    done[st] = 0;
-                    if (q + nstages < nsteps) issue(q + nstages, st);
-                }
-            }
+            ph_b ^= 1u << bslot; // every step completes its bar_base slot exactly once, waited for or not
+            if (!sparse) release_stage(); // a dense warp stores straight out of the stage
             if (REFREG) ++t;
             else if (++s == p.nseg) { s = 0; ++t; }
             if (++st == nstages) st = 0;

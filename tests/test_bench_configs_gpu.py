@@ -156,3 +156,29 @@ def test_real_camera_frames_full_size(cvs, oracle):
     assert pos == opos and np.array_equal(xs, oxs) and np.array_equal(diff, odiff)
     assert np.array_equal(s.reference(), oref)
     s.close()
+
+
+@pytest.mark.parametrize("w,h,mode", [(2560, 1440, 0), (3001, 1999, 0), (3001, 1999, 2), (2561, 1441, 5)])
+def test_banded_sequences_odd_sizes(cvs, oracle, w, h, mode):
+    # frames that take more than one pass of the grid are walked band by band when a sequence is long enough (every
+    # band = one launch with the reference in registers, counts handed from band to band): sizes whose last band is
+    # shorter than the others and whose byte count is not a multiple of the 96-byte chunk
+    import torch
+    T = 5
+    n = 3 * w * h
+    fr, stride = _device_sequence(cvs, torch, w, h, T, 60000, BENCH_SEED ^ 7)
+    base = fr[:n].cpu().numpy()
+    s = cvs.Stream(w, h, base, mode=mode, max_sequence=T)
+    pos, d_xs, d_diff, d_show, cap = _run(cvs, torch, s, fr, stride, T, n, mode)
+    oc = oracle.OracleCore(w, h, base, mode=mode)
+    for t in range(T):
+        cur = fr[(t + 1) * stride:(t + 1) * stride + n].cpu().numpy()
+        opos, oxs, odiff, oshow, _ = oc.exec_core(cur)
+        assert pos[t] == opos, f"frame {t}: pos {pos[t]} != {opos}"
+        assert np.array_equal(d_xs[t * cap:t * cap + opos].cpu().numpy(), oxs), f"frame {t}: xs"
+        assert np.array_equal(d_diff[t * cap:t * cap + opos].cpu().numpy(), odiff), f"frame {t}: diff"
+        if mode:
+            assert np.array_equal(d_show[t * stride:t * stride + n].cpu().numpy(), oshow), f"frame {t}: show"
+    assert np.array_equal(s.reference(), oc.reference())
+    s.close()
+    oc.close()
