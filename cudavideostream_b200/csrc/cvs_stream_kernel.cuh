@@ -214,10 +214,11 @@ __device__ __forceinline__ uint8_t *at_u8(uint8_t *base, uint32_t i)
 // (the warp's staging window, idle in a dense step): one broadcast 16-byte and one 8-byte shared load per chunk
 // instead of shuffles and popcounts.  CHECK = false when the warp's whole run fits the payload capacity.
 // This loop is the bulk of a dense frame's instructions.
+// nchunk: chunks the warp holds (lanes >= nchunk have an empty mask); a multiple of the batch size.
 template <bool CHECK>
 __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
                                           int *xs_out, uint8_t *df_out, uint32_t g_lane, uint32_t cap32, uint32_t lane,
-                                          uint32_t scratch)
+                                          uint32_t scratch, uint32_t nchunk = 32)
 {
     {
         const uint32_t r1 = g_lane + (uint32_t)__popc(m[0]), r2 = r1 + (uint32_t)__popc(m[1]);
@@ -233,7 +234,7 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
 #endif
     constexpr int kBatch = CVS_COOP_BATCH; // chunks in flight: their shared loads are issued before any store
 #pragma unroll 1
-    for (uint32_t S0 = 0; S0 < 32; S0 += kBatch) {
+    for (uint32_t S0 = 0; S0 < nchunk; S0 += kBatch) {
         uint32_t sm[kBatch][kMaskWords], rk[kBatch][kMaskWords], v[kBatch][kMaskWords];
 #pragma unroll
         for (int i = 0; i < kBatch; i++) {

@@ -133,7 +133,14 @@ template <int MODE, bool HI, bool REFREG>
 __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // role of a warp: the scheduler arbitrates highest-warp-id-first, so which group gets the upper half decides who
+    // wins when both want an issue slot
+#ifdef CVS_WS_FRONT_HIGH
+    const uint32_t tid = threadIdx.x ^ (uint32_t)kWsFrontThreads; // front = hardware warps 16..31
+#else
+    const uint32_t tid = threadIdx.x;
+#endif
+    const uint32_t lane = tid & 31, warp = tid >> 5;
     const uint32_t b = blockIdx.x, G = gridDim.x;
     const uint32_t N = p.nbytes;
     const uint32_t nsteps = (uint32_t)p.nframes * p.nseg;
@@ -355,17 +362,33 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                     }
                 }
             }
-            if (kStreamLoad && nv) {
-                uint4 nx = lds128(myaddr + voff(0));
+#ifdef CVS_PROFILING
+            if (p.debug & 4u) nv = 0; // timing experiment: ingest only (results wrong by construction)
+#endif
+            if (kStreamLoad && nv == (uint32_t)kChunkBytes) {
+                // the common case as ONE basic block (no per-vector test for the end of the frame), two vectors of look-ahead:
+                // the scheduler can interleave the six independent vector passes, which is what hides the ALU latency with
+                // only 3.5 front warps per scheduler
+                uint4 n0 = lds128(myaddr + voff(0)), n1 = lds128(myaddr + voff(1));
 #pragma unroll
                 for (int v = 0; v < kChunkWords / 4; v++) {
-                    uint32_t cv[4] = {nx.x, nx.y, nx.z, nx.w};
-                    if (v + 1 < kChunkWords / 4) nx = lds128(myaddr + voff(v + 1));
-                    if (__builtin_expect(nv < (uint32_t)kChunkBytes, 0)) {
+                    const uint32_t cv[4] = {n0.x, n0.y, n0.z, n0.w};
+                    n0 = n1;
+                    if (v + 2 < kChunkWords / 4) n1 = lds128(myaddr + voff(v + 2));
+                    pass_vector(v, cv);
+                }
+            } else if (kStreamLoad && nv) {
+                // the chunk that holds the end of the frame
+#pragma unroll 1
+                for (int pass = 0; pass < 1; pass++) {
+#pragma unroll
+                    for (int v = 0; v < kChunkWords / 4; v++) {
+                        const uint4 nx = lds128(myaddr + voff(v));
+                        uint32_t cv[4] = {nx.x, nx.y, nx.z, nx.w};
 #pragma unroll
                         for (int h = 0; h < 4; h++) cv[h] = clip_word(4 * v + h, cv[h]);
+                        pass_vector(v, cv);
                     }
-                    pass_vector(v, cv);
                 }
             }
             if (sw) { // slot order -> byte order: rotate the 96-bit mask by 48
@@ -430,8 +453,14 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
         // BACK: block scan, cross-block look-back, emission of the (index, value) entries
         // =====================================================================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CVS_WS_BACK_REGS));
-        const uint32_t bw = warp - kWsFrontWarps;     // front warp whose chunks this warp emits
-        const uint32_t ftid = bw * 32 + lane;         // front thread whose chunk this lane emits
+        // back warp w emits the chunks front warp w holds.  (Dealing the block's chunks out evenly to all sixteen back
+        // warps -- 28 each at 1080p instead of 32 for 13.7 warps -- measured 1 % faster at 50 % density but 6-9 % slower
+        // at 1 % and 10 %: the two otherwise idle warps then compete with the front for issue slots.)
+        const uint32_t bw = warp - kWsFrontWarps;
+        const uint32_t per = 32;
+        const uint32_t c0 = per * bw;                 // first chunk (= front thread) of this warp
+        const uint32_t ftid = c0 + lane;              // front thread whose chunk this lane emits
+        const bool has_chunk = ftid < nact;
         const bool scan_warp = bw == (uint32_t)kWsBackWarps - 1;
         uint16_t *sxs = reinterpret_cast<uint16_t *>(smem + WsLayout::sxs) + bw * SmemLayout::kXsHalves;
         uint8_t *sd = smem + WsLayout::sd + bw * SmemLayout::kSdBytes;
@@ -440,7 +469,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
         uint32_t ph_f = 0, ph_b = 0, st = 0, t = 0, s = 0;
         for (uint32_t q = 0; q < nsteps; q++) {
             // byte offset of lane 0's chunk in the frame (chunk S of the warp starts 96*S bytes later)
-            const uint32_t wcoff = p.index_base + (uint32_t)((((uint64_t)s * G + b) * p.cps + bw * 32) * kChunkBytes);
+            const uint32_t wcoff = p.index_base + (uint32_t)((((uint64_t)s * G + b) * p.cps + c0) * kChunkBytes);
             // global-offset slot of the step: 2 x nstages slots, because a sparse warp lets its stage go before it waits
             // for the offset, so the look-back warp may be up to nstages steps ahead of it (not more: the bulk copy of
             // step q + nstages + 1 needs this warp's release of step q + 1)
@@ -448,18 +477,57 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
             wait_bar(bar_fdone + 8 * st, (ph_f >> st) & 1u, CVS_WS_SLEEP_BACK);
             ph_f ^= 1u << st;
             uint32_t m[kMaskWords] = {0, 0, 0}, cnt = 0;
-            if (ftid < nact)
+            if (has_chunk)
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(m[0]), "=r"(m[1]), "=r"(m[2]), "=r"(cnt)
                              : "r"(msk_addr + st * msk_stride + 16 * ftid)
                              : "memory");
-            uint32_t wexc, total;
+            uint32_t wexc, total; // entries of the block in front of this warp's chunks / of the whole block
             {
                 const uint32_t v = lane < (uint32_t)kWsFrontWarps ? wtot[st * 16 + lane] : 0u;
                 total = warp_add(v);
                 wexc = warp_add(lane < bw ? v : 0u);
             }
+            const uint32_t incl = warp_incl_scan(cnt, lane);
+            const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t wrank = incl - cnt;
+            const uint32_t dv0 = stage_addr + st * stage_bytes + c0 * kChunkBytes; // parked bytes of lane 0's chunk
+            // this warp is done with the ring stage; the last warp to say so refills it
+            auto release_stage = [&]() {
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    if (atomicAdd(&done[st], 1u) == (uint32_t)kWsBackWarps - 1u) {
+                        done[st] = 0;
+                        if (q + nstages < nsteps) issue(q + nstages, st);
+                    }
+                }
+            };
+            // A warp whose entries fit its window copies them out of the stage NOW, in rank order, and lets the stage
+            // go before it waits for the block's global offset: the look-back latency is then outside the stage's
+            // lifetime (bulk copy -> pass -> this copy), which is what bounds the step rate with four stages.
+            const bool sparse = wtotal <= (uint32_t)kWarpEntries;
+#ifdef CVS_PROFILING
+            if (p.debug & 2u) { // timing experiment: no emission at all (results wrong by construction)
+                release_stage();
+                ph_b ^= 1u << bslot;
+                if (REFREG) ++t;
+                else if (++s == p.nseg) { s = 0; ++t; }
+                if (++st == nstages) st = 0;
+                continue;
+            }
+#endif
+            if (sparse) {
+                if (wtotal) {
+                    uint32_t o = wrank;
+#pragma unroll
+                    for (int w = 0; w < kMaskWords; w++)
+                        emit_bits(m[w], 32 * w, lane * kChunkBytes, dv0 + lane * kChunkBytes, sxs, sd, o);
+                }
+                release_stage();
+            }
             if (scan_warp) {
+                // (after this warp has let go of the stage: the look-back must not sit inside the stage's lifetime)
                 // ---- cross-block exchange of the step: sum the predecessors' totals (each lane reads up to kWsLook
                 //      descriptors, all in flight together: one L2 round trip)
                 unsigned long long *row = p.desc + (size_t)q * (G + 1); // (the block's own total was published by the front)
@@ -501,34 +569,6 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                     mbar_arrive(bar_base + 8 * bslot);
                 }
             }
-            const uint32_t incl = warp_incl_scan(cnt, lane);
-            const uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t wrank = incl - cnt;
-            const uint32_t dv0 = stage_addr + st * stage_bytes + bw * 32 * kChunkBytes; // parked bytes of lane 0's chunk
-            // this warp is done with the ring stage; the last warp to say so refills it
-            auto release_stage = [&]() {
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence_block();
-                    if (atomicAdd(&done[st], 1u) == (uint32_t)kWsBackWarps - 1u) {
-                        done[st] = 0;
-                        if (q + nstages < nsteps) issue(q + nstages, st);
-                    }
-                }
-            };
-            // A warp whose entries fit its window copies them out of the stage NOW, in rank order, and lets the stage
-            // go before it waits for the block's global offset: the look-back latency is then outside the stage's
-            // lifetime (bulk copy -> pass -> this copy), which is what bounds the step rate with four stages.
-            const bool sparse = wtotal <= (uint32_t)kWarpEntries;
-            if (sparse) {
-                if (wtotal) {
-                    uint32_t o = wrank;
-#pragma unroll
-                    for (int w = 0; w < kMaskWords; w++)
-                        emit_bits(m[w], 32 * w, lane * kChunkBytes, dv0 + lane * kChunkBytes, sxs, sd, o);
-                }
-                release_stage();
-            }
             if (wtotal) {
                 wait_bar(bar_base + 8 * bslot, (ph_b >> bslot) & 1u, CVS_WS_SLEEP_BACK);
                 const uint32_t base = *reinterpret_cast<volatile uint32_t *>(sbase + bslot);
@@ -540,9 +580,9 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                     flush_warp_shifted(sxs, sd, wcoff, xs_out, df_out, g0, wtotal, p.cap, lane);
                     __syncwarp(); // the window is refilled by the next step
                 } else if (g0 + wtotal <= (size_t)cap32) {
-                    emit_coop<false>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
+                    emit_coop<false>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs), per);
                 } else {
-                    emit_coop<true>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs));
+                    emit_coop<true>(m, wcoff, dv0, xs_out, df_out, (uint32_t)g0 + wrank, cap32, lane, smem_u32(sxs), per);
                 }
             }
             ph_b ^= 1u << bslot; // every step completes its bar_base slot exactly once, waited for or not
