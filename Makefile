@@ -8,7 +8,7 @@ all: lib oracle
 lib: $(LIB)
 $(LIB): $(wildcard $(CSRC)/*.cu $(CSRC)/*.cuh include/*.h include/*.hpp)
 	$(NVCC) -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden \
-	    -shared -cudart shared -I include -o $@ $(CSRC)/cvs_api.cu $(CSRC)/cvs_shim.cu
+	    -shared -cudart shared -I include -o $@ $(CSRC)/cvs_api.cu $(CSRC)/cvs_shim.cu -ldl
 
 oracle:
 	$(MAKE) -C oracle -s all

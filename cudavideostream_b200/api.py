@@ -74,6 +74,8 @@ SIGNATURES = {
     "cvs_wire_encode_device": (C.c_int, [_vp, _vp, _vp, _sz, C.c_int, C.c_int, _vp, _vp, _vp]),
     "cvs_wire_decode_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "cvs_wire_decode_status": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "cvs_submit_jpeg": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_char_p, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "cvs_decode_jpeg_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "cvs_synth_base_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, _vp]),
     "cvs_synth_next_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
 }
@@ -189,6 +191,17 @@ class Stream:
         t = C.c_uint64(0)
         _check(load_library().cvs_submit_wire(self._h, frame_ptr, wire_ptr, show_ptr, text.encode(), C.byref(t)))
         return t.value
+
+    def submit_jpeg_raw(self, jpeg_ptr: int, jpeg_bytes: int, diff_ptr: int, show_ptr, text: str, pos_ptr: int, xs_ptr: int) -> int:
+        """cvs_submit_jpeg: the frame arrives as the camera's JPEG bitstream and is decoded on the GPU (nvJPEG)."""
+        t = C.c_uint64(0)
+        _check(load_library().cvs_submit_jpeg(self._h, jpeg_ptr, jpeg_bytes, diff_ptr, show_ptr, text.encode(), pos_ptr, xs_ptr,
+                                              C.byref(t)))
+        return t.value
+
+    def decode_jpeg_device(self, jpeg: bytes, d_out: int, cuda_stream: int = 0) -> None:
+        buf = (C.c_uint8 * len(jpeg)).from_buffer_copy(jpeg)
+        _check(load_library().cvs_decode_jpeg_device(self._h, C.addressof(buf), len(jpeg), d_out, cuda_stream or None))
 
     def wait(self, ticket: int) -> None:
         _check(load_library().cvs_wait(self._h, ticket))

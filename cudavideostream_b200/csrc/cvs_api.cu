@@ -6,6 +6,8 @@
 #include "../../include/cvs_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h>
 
 #include <atomic>
 #include <cmath>
@@ -105,6 +107,50 @@ int grid_for(size_t items, int block, int sms)
     return (int)blocks;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// nvJPEG, loaded on first use (dlopen: libcvs_b200.so has no link-time dependency on it).  Used by cvs_submit_jpeg /
+// cvs_decode_jpeg_device: the capture side of the reference delivers MJPG (server/src/threads.cpp:32-41) and decodes
+// it on the CPU; decoding on the GPU replaces the 6.2 MB host-to-device copy of a raw 1080p frame by the ~0.4 MB
+// bitstream.  The decode itself is the library's (like calling cuBLAS); everything after it is this library's path.
+// ---------------------------------------------------------------------------------------------------------------
+struct NvJpegApi {
+    void *lib = nullptr;
+    nvjpegStatus_t (*CreateEx)(nvjpegBackend_t, nvjpegDevAllocator_t *, nvjpegPinnedAllocator_t *, unsigned int, nvjpegHandle_t *) = nullptr;
+    nvjpegStatus_t (*CreateSimple)(nvjpegHandle_t *) = nullptr;
+    nvjpegStatus_t (*Destroy)(nvjpegHandle_t) = nullptr;
+    nvjpegStatus_t (*StateCreate)(nvjpegHandle_t, nvjpegJpegState_t *) = nullptr;
+    nvjpegStatus_t (*StateDestroy)(nvjpegJpegState_t) = nullptr;
+    nvjpegStatus_t (*GetImageInfo)(nvjpegHandle_t, const unsigned char *, size_t, int *, nvjpegChromaSubsampling_t *, int *, int *) = nullptr;
+    nvjpegStatus_t (*Decode)(nvjpegHandle_t, nvjpegJpegState_t, const unsigned char *, size_t, nvjpegOutputFormat_t, nvjpegImage_t *,
+                             cudaStream_t) = nullptr;
+    bool ok = false;
+};
+std::mutex g_nvjpeg_mutex;
+NvJpegApi g_nvjpeg;
+
+const NvJpegApi *nvjpeg_api()
+{
+    std::lock_guard<std::mutex> lk(g_nvjpeg_mutex);
+    NvJpegApi &a = g_nvjpeg;
+    if (a.ok) return &a;
+    if (!a.lib) {
+        for (const char *name : {"libnvjpeg.so.12", "libnvjpeg.so", "/usr/local/cuda/lib64/libnvjpeg.so.12"}) {
+            a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (a.lib) break;
+        }
+    }
+    if (!a.lib) return nullptr;
+    a.CreateEx = (decltype(a.CreateEx))dlsym(a.lib, "nvjpegCreateEx");
+    a.CreateSimple = (decltype(a.CreateSimple))dlsym(a.lib, "nvjpegCreateSimple");
+    a.Destroy = (decltype(a.Destroy))dlsym(a.lib, "nvjpegDestroy");
+    a.StateCreate = (decltype(a.StateCreate))dlsym(a.lib, "nvjpegJpegStateCreate");
+    a.StateDestroy = (decltype(a.StateDestroy))dlsym(a.lib, "nvjpegJpegStateDestroy");
+    a.GetImageInfo = (decltype(a.GetImageInfo))dlsym(a.lib, "nvjpegGetImageInfo");
+    a.Decode = (decltype(a.Decode))dlsym(a.lib, "nvjpegDecode");
+    a.ok = a.CreateSimple && a.Destroy && a.StateCreate && a.StateDestroy && a.GetImageInfo && a.Decode;
+    return a.ok ? &a : nullptr;
+}
+
 constexpr int kSlots = 4; // tickets that may be outstanding per stream
 
 struct Slot {
@@ -116,6 +162,7 @@ struct Slot {
     unsigned int *h_pos = nullptr; // pinned
     uint32_t *d_starts = nullptr;     // compact wire format: entries before each tile (ntiles + 2 words), on first use
     uint8_t *d_wire = nullptr;        // compact wire format: encoded frame when the caller's buffer is not mapped
+    nvjpegJpegState_t jpeg_state = nullptr; // cvs_submit_jpeg: decoder state of this slot (on first use)
     uint8_t *u_wire = nullptr;        // caller's buffer of a cvs_submit_wire ticket (nullptr: reference-format ticket)
     unsigned int *d_status = nullptr; // StatusBits of this ticket's launches (cleared at submit)
     unsigned int *h_status = nullptr; // pinned copy, valid once ev_pos has fired
@@ -223,6 +270,8 @@ struct cvs_stream_s {
     unsigned int *h_status = nullptr; // pinned
     unsigned long long *d_desc = nullptr;
     size_t desc_words = 0;
+    nvjpegHandle_t jpeg = nullptr;      // cvs_submit_jpeg / cvs_decode_jpeg_device: nvJPEG handle (on first use)
+    nvjpegJpegState_t jpeg_state = nullptr; // decoder state of cvs_decode_jpeg_device
     unsigned int *d_band_pos = nullptr; // banded launches: two arrays of per-frame counts so far (ping-pong)
     size_t band_frames = 0;
     uint32_t epoch = 0;
@@ -453,6 +502,8 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         if (h->d_band_pos) {
             CU_TRY(cudaDeviceSynchronize());
             cudaFree(h->d_band_pos);
+    if (h->jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(h->jpeg_state);
+    if (h->jpeg && g_nvjpeg.ok) g_nvjpeg.Destroy(h->jpeg);
             h->d_band_pos = nullptr;
             h->band_frames = 0;
         }
@@ -745,12 +796,15 @@ cvs_status cvs_destroy(cvs_handle h)
         cudaFreeHost(s.h_status);
         cudaFree(s.d_starts);
         cudaFree(s.d_wire);
+        if (s.jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(s.jpeg_state);
         cudaEvent_t evs[] = {s.ev_h2d0, s.ev_h2d1, s.ev_k0, s.ev_k1, s.ev_pos, s.ev_p0, s.ev_done};
         for (cudaEvent_t e : evs)
             if (e) cudaEventDestroy(e);
     }
     cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
     cudaFree(h->d_band_pos);
+    if (h->jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(h->jpeg_state);
+    if (h->jpeg && g_nvjpeg.ok) g_nvjpeg.Destroy(h->jpeg);
     cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
     cudaFree(h->d_glyphs);
     if (h->s_comp) cudaStreamDestroy(h->s_comp);
@@ -789,8 +843,40 @@ cvs_status cvs_free_host(void *ptr)
 
 // common body of cvs_submit / cvs_submit_io (reference-format payload into diff_out / xs / pos) and cvs_submit_wire
 // (wire_out != nullptr: compact "CVW1" frame, see cvs_filter_kernels.cuh)
+// decode one baseline JPEG of the stream's frame size into d_out (BGR interleaved, pitch 3*width), asynchronously on `st`
+static cvs_status jpeg_decode(cvs_handle h, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
+                              cudaStream_t st)
+{
+    const NvJpegApi *nj = nvjpeg_api();
+    if (!nj) return fail(CVS_ERR_NODEVICE, "libnvjpeg could not be loaded: %s", dlerror());
+    if (!h->jpeg) {
+        // GPU-assisted Huffman decoding where the library offers it, else its default backend
+        nvjpegStatus_t e = nj->CreateEx ? nj->CreateEx(NVJPEG_BACKEND_GPU_HYBRID, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &h->jpeg)
+                                        : NVJPEG_STATUS_NOT_INITIALIZED;
+        if (e != NVJPEG_STATUS_SUCCESS) e = nj->CreateSimple(&h->jpeg);
+        if (e != NVJPEG_STATUS_SUCCESS) return fail(CVS_ERR_CUDA, "nvjpegCreate failed (%d)", (int)e);
+    }
+    if (!*state) {
+        const nvjpegStatus_t e = nj->StateCreate(h->jpeg, state);
+        if (e != NVJPEG_STATUS_SUCCESS) return fail(CVS_ERR_CUDA, "nvjpegJpegStateCreate failed (%d)", (int)e);
+    }
+    int ncomp = 0, widths[NVJPEG_MAX_COMPONENT] = {0}, heights[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    nvjpegStatus_t e = nj->GetImageInfo(h->jpeg, jpeg, jpeg_bytes, &ncomp, &sub, widths, heights);
+    if (e != NVJPEG_STATUS_SUCCESS) return fail(CVS_ERR_INVALID, "not a decodable JPEG (nvjpegGetImageInfo %d)", (int)e);
+    if (widths[0] != h->width || heights[0] != h->height)
+        return fail(CVS_ERR_INVALID, "JPEG is %dx%d, the stream is %dx%d", widths[0], heights[0], h->width, h->height);
+    nvjpegImage_t img;
+    memset(&img, 0, sizeof img);
+    img.channel[0] = d_out;
+    img.pitch[0] = (size_t)3 * h->width;
+    e = nj->Decode(h->jpeg, *state, jpeg, jpeg_bytes, NVJPEG_OUTPUT_BGRI, &img, st);
+    if (e != NVJPEG_STATUS_SUCCESS) return fail(CVS_ERR_CUDA, "nvjpegDecode failed (%d)", (int)e);
+    return CVS_OK;
+}
+
 static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
-                                unsigned int *pos, int *xs, uint8_t *wire_out, uint64_t *ticket)
+                                unsigned int *pos, int *xs, uint8_t *wire_out, uint64_t *ticket, size_t jpeg_bytes = 0)
 {
     cvs_status st = check_handle(h);
     if (st) return st;
@@ -804,9 +890,14 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     }
 
     const double th0 = h->trace ? host_us() : 0;
-    // H2D (kernels.cu:461)
+    // H2D (kernels.cu:461) -- of the raw frame, or of the camera's JPEG bitstream, decoded on the device
     CU_TRY(cudaEventRecord(s.ev_h2d0, h->s_h2d));
-    CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
+    if (jpeg_bytes) {
+        st = jpeg_decode(h, &s.jpeg_state, frame, jpeg_bytes, s.d_in, h->s_h2d);
+        if (st) return st;
+    } else {
+        CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
+    }
     CU_TRY(cudaEventRecord(s.ev_h2d1, h->s_h2d));
     // kernels
     CU_TRY(cudaStreamWaitEvent(h->s_comp, s.ev_h2d1, 0));
@@ -895,6 +986,21 @@ cvs_status cvs_submit_io(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, 
                          unsigned int *pos, int *xs, uint64_t *ticket)
 {
     return submit_common(h, frame, diff_out, show, text, pos, xs, nullptr, ticket);
+}
+
+cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *diff_out, uint8_t *show,
+                           const char *text, unsigned int *pos, int *xs, uint64_t *ticket)
+{
+    if (!jpeg || jpeg_bytes == 0) return fail(CVS_ERR_INVALID, "null argument");
+    return submit_common(h, jpeg, diff_out, show, text, pos, xs, nullptr, ticket, jpeg_bytes);
+}
+
+cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out, void *cuda_stream)
+{
+    cvs_status st = check_handle(h);
+    if (st) return st;
+    if (!jpeg || jpeg_bytes == 0 || !d_out) return fail(CVS_ERR_INVALID, "null argument");
+    return jpeg_decode(h, &h->jpeg_state, jpeg, jpeg_bytes, d_out, (cudaStream_t)cuda_stream);
 }
 
 cvs_status cvs_submit_wire(cvs_handle h, const uint8_t *frame, uint8_t *wire_out, uint8_t *show, const char *text,

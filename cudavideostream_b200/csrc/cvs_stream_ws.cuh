@@ -453,9 +453,12 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
         // BACK: block scan, cross-block look-back, emission of the (index, value) entries
         // =====================================================================================================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CVS_WS_BACK_REGS));
-        // back warp w emits the chunks front warp w holds.  (Dealing the block's chunks out evenly to all sixteen back
-        // warps -- 28 each at 1080p instead of 32 for 13.7 warps -- measured 1 % faster at 50 % density but 6-9 % slower
-        // at 1 % and 10 %: the two otherwise idle warps then compete with the front for issue slots.)
+        // back warp w emits the chunks front warp w holds.  Measured and rejected (round 2, us per 1080p frame at
+        // 1 / 10 / 50 % against 2.18 / 2.97 / 5.72): dealing the block's chunks out evenly to all sixteen back warps (28
+        // each instead of 32 for 13.7 warps) 2.31 / 3.25 / 5.67 -- the look-back warp then has entries of its own and
+        // starts the next look-back late; letting the front warp store the upper half of its own chunks in dense steps
+        // (ranks scanned by the front, posted in the mask queue) 2.36 / 2.88 / 7.53 -- the front then waits for the
+        // global offset and its next pass starts late, so pass and emission no longer overlap.
         const uint32_t bw = warp - kWsFrontWarps;
         const uint32_t per = 32;
         const uint32_t c0 = per * bw;                 // first chunk (= front thread) of this warp

@@ -229,6 +229,21 @@ cvs_status cvs_wire_decode_device(const uint8_t *d_wire, uint32_t *d_scratch, ui
                                   void *cuda_stream);
 cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int height, void *cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Capture-side decode on the GPU.  The reference's camera delivers MJPG and OpenCV
+ * decodes it on the CPU before exec_core sees the frame (server/src/threads.cpp:32-41; "read 37 ms",
+ * REPORT/report.tex:914).  cvs_submit_jpeg takes the camera's JPEG bitstream instead of the decoded frame: ~0.4 MB
+ * cross PCIe instead of 6.2 MB (1080p), nvJPEG (loaded with dlopen on first use) decodes into the slot's upload
+ * buffer and the rest of the path is unchanged.  The decoder is NVIDIA's, not libjpeg-turbo: decoded pixels can differ
+ * from OpenCV's by a few LSB (tests/test_jpeg_ingest.py measures it on the reference's own f1.jpg / f2.jpg), so a
+ * payload produced this way equals the reference's only up to the decoder -- opt-in, like the wire format.
+ * --------------------------------------------------------------------------------------------------------------- */
+cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *diff_out, uint8_t *show,
+                           const char *text, unsigned int *pos, int *xs, uint64_t *ticket);
+/* the decode alone: baseline JPEG of the stream's frame size -> BGR24 frame in device memory (N bytes) */
+cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
+                                  void *cuda_stream);
+
 /* Synthetic camera used by bench.py and the parity tests: counter-based
  * splitmix64 so that the numpy twin in cudavideostream_b200/synth.py produces identical bytes.
  *   cvs_synth_base_device   : base frame (diagonal gradient + noise)

@@ -1,0 +1,98 @@
+"""Capture-side decode on the GPU: cvs_submit_jpeg takes the camera's JPEG bitstream
+(the reference's camera delivers MJPG, server/src/threads.cpp:32-41) and decodes it with nvJPEG on the device.
+
+What is checked bit for bit: given the pixels the GPU decoder produced, the payload, count and new reference are
+exactly the oracle's.  What is only MEASURED (and bounded loosely): how far nvJPEG's pixels are from OpenCV's
+(libjpeg-turbo) on the reference's own fixture frames -- the two decoders are different implementations of the IDCT /
+chroma upsampling, so a payload produced through this entry point equals the reference's only up to the decoder."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _jpeg(name):
+    with open(os.path.join(GOLDEN, name), "rb") as f:
+        return f.read()
+
+
+def test_jpeg_ingest_on_the_reference_camera_frames(cvs, oracle):
+    import torch
+    w, h = 1920, 1080
+    n = 3 * w * h
+    j1, j2 = _jpeg("k1_f1.jpg"), _jpeg("k1_f2.jpg")
+    st = torch.cuda.current_stream().cuda_stream
+    s0 = cvs.Stream(w, h, np.zeros(n, dtype=np.uint8))
+    d = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+    try:
+        s0.decode_jpeg_device(j1, d.data_ptr(), st)
+    except cvs.CVSError as e:
+        if e.status == 6:
+            pytest.skip(f"nvJPEG is not available on this box: {e}")
+        raise
+    torch.cuda.synchronize()
+    g1 = d[:n].cpu().numpy().copy()
+    s0.decode_jpeg_device(j2, d.data_ptr(), st)
+    torch.cuda.synchronize()
+    g2 = d[:n].cpu().numpy().copy()
+    s0.close()
+
+    # ---- the path behind the decoder is bit-exact: same pixels in, oracle's payload out
+    s = cvs.Stream(w, h, g1)
+    jb = cvs.alloc_host(len(j2) + 64)
+    jb.array()[:len(j2)] = np.frombuffer(j2, dtype=np.uint8)
+    dout, xout, pb = cvs.alloc_host(n + 32), cvs.alloc_host(4 * n + 32), (C.c_uint * 1)()
+    for rep in range(2):  # second submission: same frame against the updated reference
+        tk = s.submit_jpeg_raw(jb.ptr, len(j2), dout.ptr, None, "", C.addressof(pb), xout.ptr)
+        s.wait(tk)
+        if rep == 0:
+            opos, oxs, odiff, oref, _ = oracle.diff_compact(g2, g1, 20)
+        else:
+            opos, oxs, odiff, oref, _ = oracle.diff_compact(g2, oref, 20)
+        assert pb[0] == opos, f"submission {rep}"
+        assert np.array_equal(dout.array()[:opos], odiff) and np.array_equal(xout.array(np.int32)[:opos], oxs)
+        assert np.array_equal(s.reference(), oref)
+    s.close()
+
+    # ---- how close is the GPU decoder to the reference's CPU decode (OpenCV / libjpeg-turbo)?
+    cv2 = pytest.importorskip("cv2")
+    c1 = cv2.imread(os.path.join(GOLDEN, "k1_f1.jpg")).reshape(-1)
+    c2 = cv2.imread(os.path.join(GOLDEN, "k1_f2.jpg")).reshape(-1)
+    d1 = np.abs(g1.astype(np.int16) - c1.astype(np.int16))
+    d2 = np.abs(g2.astype(np.int16) - c2.astype(np.int16))
+    with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
+        k1 = json.load(f)["changed_bytes"]
+    gpos = oracle.count_difference(g1, g2, 20)
+    print(f"\nnvJPEG vs OpenCV decode: f1 max |d| {d1.max()} mean {d1.mean():.4f} differing bytes {100.0 * (d1 > 0).mean():.2f} %; "
+          f"f2 max |d| {d2.max()} mean {d2.mean():.4f} differing {100.0 * (d2 > 0).mean():.2f} %; "
+          f"changed bytes f1->f2: {gpos} with the GPU decode, {k1} with OpenCV's (REPORT/report.tex:2594)")
+    assert d1.mean() < 2.0 and d2.mean() < 2.0, "the GPU decode is not the same picture"
+    assert abs(gpos - k1) < 0.1 * k1
+
+
+def test_jpeg_ingest_rejects_other_sizes_and_garbage(cvs):
+    w, h = 640, 360
+    s = cvs.Stream(w, h, np.zeros(3 * w * h, dtype=np.uint8))
+    j = _jpeg("k1_f1.jpg")  # 1920x1080
+    jb = cvs.alloc_host(len(j) + 64)
+    jb.array()[:len(j)] = np.frombuffer(j, dtype=np.uint8)
+    n = 3 * w * h
+    dout, xout, pb = cvs.alloc_host(n + 32), cvs.alloc_host(4 * n + 32), (C.c_uint * 1)()
+    with pytest.raises(cvs.CVSError) as e:
+        s.submit_jpeg_raw(jb.ptr, len(j), dout.ptr, None, "", C.addressof(pb), xout.ptr)
+    if e.value.status == 6:
+        pytest.skip("nvJPEG is not available on this box")
+    assert e.value.status == 1  # CVS_ERR_INVALID: the JPEG is 1920x1080, the stream 640x360
+    jb.array()[:64] = 0x55
+    with pytest.raises(cvs.CVSError):
+        s.submit_jpeg_raw(jb.ptr, 64, dout.ptr, None, "", C.addressof(pb), xout.ptr)
+    # the handle is still usable afterwards
+    f = np.full(n, 77, dtype=np.uint8)
+    pos, xs, diff, _ = s.exec(f)
+    assert pos == n
+    s.close()
