@@ -71,8 +71,9 @@ def test_jpeg_ingest_on_the_reference_camera_frames(cvs, oracle):
     print(f"\nnvJPEG vs OpenCV decode: f1 max |d| {d1.max()} mean {d1.mean():.4f} differing bytes {100.0 * (d1 > 0).mean():.2f} %; "
           f"f2 max |d| {d2.max()} mean {d2.mean():.4f} differing {100.0 * (d2 > 0).mean():.2f} %; "
           f"changed bytes f1->f2: {gpos} with the GPU decode, {k1} with OpenCV's (REPORT/report.tex:2594)")
-    assert d1.mean() < 2.0 and d2.mean() < 2.0, "the GPU decode is not the same picture"
-    assert abs(gpos - k1) < 0.1 * k1
+    # with interpolating chroma upsampling (the library default here): max |d| 5, mean 0.64, K1 370,732 vs 369,350
+    assert d1.mean() < 1.0 and d2.mean() < 1.0 and d1.max() <= 8 and d2.max() <= 8, "the GPU decode is not the same picture"
+    assert abs(gpos - k1) < 0.01 * k1
 
 
 def test_jpeg_ingest_rejects_other_sizes_and_garbage(cvs):
