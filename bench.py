@@ -53,6 +53,9 @@ def workload_config(frames: int) -> dict:
     return {"workload": "%s_seq%d_d1_10_50" % (name, frames), "width": W, "height": H, "threshold": THR,
             "frames_per_sequence": frames, "sequences_per_step": len(DENSITIES_PPM), "densities_ppm": list(DENSITIES_PPM),
             "seed": "0x%X" % BASE_SEED, "streams_per_gpu": len(DENSITIES_PPM),
+            "workloads": ["headline: 1080p diff+compact, 300-frame sequences at 1/10/50 % (BASELINE configs[1]; `value`)",
+                          "config3_noiseK3_gray_weighted_binarize (configs[2])", "config4_heat_map, config4_heat_map_red (configs[3])",
+                          "config5_8x3840x2160_streams, stream s on rank s mod N (configs[4])"],
             "l2": "inputs larger than L2: 3 x %.2f GB device-resident frame sequences per step" % (frames * N / 1e9)}
 
 
