@@ -260,6 +260,8 @@ struct cvs_stream_s {
     cudaEvent_t ev_base = nullptr;
     bool push_payload = true; // CVS_PAYLOAD_PUSH=0 falls back to count round trip + copy engine
     bool speculate = true;    // CVS_EGRESS_SPECULATE=0: cvs_submit_io never copies a predicted payload size
+    bool coop = true;          // CVS_COOP=0: plain launches instead of cooperative ones (measurements only)
+    int push_blocks = 0;       // CVS_PUSH_BLOCKS: grid of the payload push kernel (0 = one block per SM)
     bool speculate_all = false; // CVS_EGRESS_SPECULATE=2: ... and 2: also for payloads above N/4 entries (measurements)
     uint32_t pred = 0;        // predicted entries of the next frame (previous count + margin)
     cvs::ConvWeights weights;
@@ -589,7 +591,10 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
             p.debug = h->debug;
             p.status = d_status;
             void *args[] = {&p};
-            CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
+            if (h->coop)
+                CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
+            else // measurement switch (CVS_COOP=0): the co-residency of the G blocks is then the caller's business
+                CU_TRY(cudaLaunchKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
             h->launches++;
         }
 
@@ -711,6 +716,8 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
         h->speculate_all = atoi(sp) == 2;
     }
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
+    if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0;
+    if (const char *pb = getenv("CVS_PUSH_BLOCKS")) h->push_blocks = atoi(pb);
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
     const cvs_status st = init_device_state(h, cfg);
@@ -992,7 +999,8 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
                    ((uintptr_t)dev_diff % 16 == 0) && ((uintptr_t)dev_xs % 16 == 0);
     }
     if (s.pushed && !wire_out) {
-        cvs::k_payload_push<<<h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, (int *)dev_xs, (uint8_t *)dev_diff, cap);
+        cvs::k_payload_push<<<h->push_blocks > 0 ? h->push_blocks : h->sms, 256, 0, h->s_d2h>>>(s.d_xs, s.d_diff, s.d_pos, (int *)dev_xs,
+                                                                                             (uint8_t *)dev_diff, cap);
         CU_TRY(cudaGetLastError());
         h->launches++;
     }
