@@ -451,14 +451,13 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
     }
 
     // ---- geometry of the persistent launch: G co-resident blocks, each owning the same cps consecutive chunks of
-    //      every frame; frames larger than G * 512 chunks take nseg passes
-    // k_stream_ws (front / back warp groups) where the reference stays in registers; frames that take several passes
-    // of the grid (3840x2160) keep the one-group kernel, which measured faster there (17 vs 25 us per frame at 1 %)
+    //      every frame.  k_stream_ws (front / back warp groups) wherever the reference can stay in registers.
     // Frames that do not fit one pass of the grid (3840x2160): a SEQUENCE is walked band by band -- every band is a
     // byte range of the frame that does fit, and one k_stream_ws launch takes that band through all frames of the
     // piece with its reference bytes in registers; frame t's entries of band j are appended behind those of the bands
-    // before it (counts handed from launch to launch).  Same payload, 1.9x faster than walking the frame in
-    // segments with the reference going through L2.  Single frames (the drop-in call) keep the one-launch kernel.
+    // before it (counts handed from launch to launch).  Same payload, 1.3-1.8x faster than walking the frame in
+    // segments with the reference going through L2, which is what single frames (the drop-in call) still do, with
+    // the one-group kernel k_stream (k_stream_ws measured 25 against 17 us per 4K frame there).
     bool ws = h->use_ws;
     int nbands = 1;
     {
@@ -510,8 +509,6 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
         if (h->d_band_pos) {
             CU_TRY(cudaDeviceSynchronize());
             cudaFree(h->d_band_pos);
-    if (h->jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(h->jpeg_state);
-    if (h->jpeg && g_nvjpeg.ok) g_nvjpeg.Destroy(h->jpeg);
             h->d_band_pos = nullptr;
             h->band_frames = 0;
         }
