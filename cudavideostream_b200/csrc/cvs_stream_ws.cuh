@@ -462,7 +462,11 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
         // each instead of 32 for 13.7 warps) 2.31 / 3.25 / 5.67 -- the look-back warp then has entries of its own and
         // starts the next look-back late; letting the front warp store the upper half of its own chunks in dense steps
         // (ranks scanned by the front, posted in the mask queue) 2.36 / 2.88 / 7.53 -- the front then waits for the
-        // global offset and its next pass starts late, so pass and emission no longer overlap.
+        // global offset and its next pass starts late, so pass and emission no longer overlap; a LAZY difference for
+        // sparse warps (the front parks current ^ reference, 7 instead of 10 ALU instructions per word, and the back warp
+        // rebuilds the few difference bytes from the frame in global memory) 3.20 / 3.08 / 5.68 -- the pass alone drops
+        // from 1.65 to 1.41 us per frame, but the scattered byte loads from L2 / HBM put more than a microsecond of
+        // latency into every step of a back warp.
         const uint32_t bw = warp - kWsFrontWarps;
         const uint32_t per = 32;
         const uint32_t c0 = per * bw;                 // first chunk (= front thread) of this warp
