@@ -88,6 +88,52 @@ __device__ __forceinline__ float byte_to_float(uint32_t word, int b) // b: compi
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u + (uint32_t)b)) - 8388608.0f;
 }
 
+// Packed pairs of floats (sm_100: FFMA2 / FADD2 work on two independent fp32 lanes held in an aligned register pair;
+// each lane is rounded exactly like the scalar instruction, so the accumulation order per output byte -- and with it
+// every bit -- is that of __fmaf_rn in row-major tap order).  One issue slot per two taps: the filter is FMA-pipe-bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi)
+{
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo2(f32x2 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float hi2(f32x2 v)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+__device__ __forceinline__ f32x2 fma2_bcast(float a, f32x2 b, f32x2 c) // {a, a} * b + c
+{
+    asm("{ .reg .b64 ra;\n mov.b64 ra, {%1, %1};\n fma.rn.f32x2 %0, ra, %2, %0; }" : "+l"(c) : "f"(a), "l"(b));
+    return c;
+}
+__device__ __forceinline__ f32x2 add2_bcast(f32x2 a, float b) // a + {b, b}, round to nearest
+{
+    f32x2 r;
+    asm("{ .reg .b64 rb;\n mov.b64 rb, {%2, %2};\n add.rn.f32x2 %0, %1, rb; }" : "=l"(r) : "l"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2_rz_bcast(f32x2 a, float b) // a + {b, b}, round towards zero
+{
+    f32x2 r;
+    asm("{ .reg .b64 rb;\n mov.b64 rb, {%2, %2};\n add.rz.f32x2 %0, %1, rb; }" : "=l"(r) : "l"(a), "f"(b));
+    return r;
+}
+
 template <int K, bool NONNEG, int WB>
 __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int width,
                                                     int height, size_t in_stride, size_t out_stride,
@@ -95,6 +141,8 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
 {
     // a thread produces WB words (4*WB bytes) x kConvRows rows; WB = 2 halves the halo conversions per output byte
     constexpr int R = K / 2, HALO = 3 * R, WL = (HALO + 3) / 4, NW = WB + 2 * WL, NB = 4 * WB, NF = NB + 2 * HALO;
+    static_assert(NF % 2 == 0, "the window is held as float pairs");
+    constexpr int NE = NF / 2, NO = NF / 2 - 1;
     const int rowbytes = 3 * width;
     const int wordsperrow = rowbytes >> 2;
     const int xw = (blockIdx.x * blockDim.x + threadIdx.x) * WB; // first word column of this thread
@@ -103,8 +151,11 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
     const uint8_t *fin = in + (size_t)blockIdx.z * in_stride;
     uint8_t *fout = out + (size_t)blockIdx.z * out_stride;
 
-    float f[K][NF]; // window: bytes x-HALO .. x+NB-1+HALO of K consecutive input rows
-    auto load_row = [&](int rr, float (&dst)[NF]) {
+    // window: bytes x-HALO .. x+NB-1+HALO of K consecutive input rows as floats, twice: fe[.][m] = (f[2m], f[2m+1]) and
+    // fo[.][m] = (f[2m+1], f[2m+2]) -- tap j of output pair (o, o+1) reads (f[o+3j], f[o+3j+1]), which starts on an odd
+    // float for odd j, and FFMA2 wants an aligned register pair.
+    f32x2 fe[K][NE], fo[K][NO > 0 ? NO : 1];
+    auto load_row = [&](int rr, f32x2 (&de)[NE], f32x2 (&dO)[NO > 0 ? NO : 1]) {
         uint32_t wd[NW];
 #pragma unroll
         for (int u = 0; u < NW; u++) {
@@ -114,39 +165,55 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
                 wd[u] = __ldg(reinterpret_cast<const uint32_t *>(fin + (size_t)rr * rowbytes) + xi);
         }
 #pragma unroll
-        for (int n = 0; n < NF; n++) {
-            const int bi = 4 * WL - HALO + n; // byte index inside wd[]
-            dst[n] = byte_to_float(wd[bi >> 2], bi & 3);
+        for (int m = 0; m < NE; m++) {
+            const int b0 = 4 * WL - HALO + 2 * m, b1 = b0 + 1; // byte indices inside wd[]
+            // the byte lands in the mantissa of 2^23; subtracting 2^23 leaves its value (exact)
+            const uint32_t u0 = __byte_perm(wd[b0 >> 2], 0x4B000000u, 0x7650u + (uint32_t)(b0 & 3));
+            const uint32_t u1 = __byte_perm(wd[b1 >> 2], 0x4B000000u, 0x7650u + (uint32_t)(b1 & 3));
+            de[m] = add2_bcast(pack2u(u0, u1), -8388608.0f);
+        }
+        // (converted again rather than copied out of de[]: two PRMT + one FADD2 land in an aligned pair directly, whereas
+        // ptxas re-creates a copied pair with two MOV at each of its three uses)
+#pragma unroll
+        for (int m = 0; m < NO; m++) {
+            const int b0 = 4 * WL - HALO + 2 * m + 1, b1 = b0 + 1;
+            const uint32_t u0 = __byte_perm(wd[b0 >> 2], 0x4B000000u, 0x7650u + (uint32_t)(b0 & 3));
+            const uint32_t u1 = __byte_perm(wd[b1 >> 2], 0x4B000000u, 0x7650u + (uint32_t)(b1 & 3));
+            dO[m] = add2_bcast(pack2u(u0, u1), -8388608.0f);
         }
     };
 #pragma unroll
-    for (int i = 0; i < K - 1; i++) load_row(row0 - R + i, f[i]);
+    for (int i = 0; i < K - 1; i++) load_row(row0 - R + i, fe[i], fo[i]);
 #pragma unroll
     for (int r = 0; r < kConvRows; r++) {
         const int row = row0 + r;
         if (row >= height) break;
-        load_row(row + R, f[(r + K - 1) % K]);
-        float acc[NB];
+        load_row(row + R, fe[(r + K - 1) % K], fo[(r + K - 1) % K]);
+        f32x2 acc[NB / 2];
 #pragma unroll
-        for (int o = 0; o < NB; o++) acc[o] = 0.f;
+        for (int o = 0; o < NB / 2; o++) acc[o] = 0ull;
 #pragma unroll
         for (int i = 0; i < K; i++)
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const float kw = w.k[i * K + j];
 #pragma unroll
-                for (int o = 0; o < NB; o++) acc[o] = __fmaf_rn(kw, f[(r + i) % K][o + 3 * j], acc[o]);
+                for (int o = 0; o < NB / 2; o++) {
+                    const int s0 = 2 * o + 3 * j; // first float of the pair
+                    acc[o] = fma2_bcast(kw, (s0 & 1) ? fo[(r + i) % K][s0 >> 1] : fe[(r + i) % K][s0 >> 1], acc[o]);
+                }
             }
         uint32_t pk[WB];
 #pragma unroll
         for (int q = 0; q < WB; q++) {
-            const float *a = acc + 4 * q;
             if (NONNEG) {
-                const uint32_t b0 = __float_as_uint(__fadd_rz(a[0], 8388608.0f)), b1 = __float_as_uint(__fadd_rz(a[1], 8388608.0f)),
-                               b2 = __float_as_uint(__fadd_rz(a[2], 8388608.0f)), b3 = __float_as_uint(__fadd_rz(a[3], 8388608.0f));
+                const f32x2 t0 = add2_rz_bcast(acc[2 * q], 8388608.0f), t1 = add2_rz_bcast(acc[2 * q + 1], 8388608.0f);
+                const uint32_t b0 = __float_as_uint(lo2(t0)), b1 = __float_as_uint(hi2(t0)), b2 = __float_as_uint(lo2(t1)),
+                               b3 = __float_as_uint(hi2(t1));
                 pk[q] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
             } else {
-                pk[q] = trunc_u8(a[0]) | (trunc_u8(a[1]) << 8) | (trunc_u8(a[2]) << 16) | (trunc_u8(a[3]) << 24);
+                pk[q] = trunc_u8(lo2(acc[2 * q])) | (trunc_u8(hi2(acc[2 * q])) << 8) | (trunc_u8(lo2(acc[2 * q + 1])) << 16) |
+                        (trunc_u8(hi2(acc[2 * q + 1])) << 24);
             }
         }
         uint32_t *dst = reinterpret_cast<uint32_t *>(fout + (size_t)row * rowbytes) + xw;

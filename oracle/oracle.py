@@ -20,8 +20,8 @@ _f32p = C.POINTER(C.c_float)
 def build(force: bool = False) -> None:
     """Compile liboracle.so / liboracle_O0.so with the Makefile next to this file."""
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "cvs_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "cvs_oracle.c"), os.path.join(_HERE, "jpeg_oracle.c"), os.path.join(_HERE, "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
 
 
@@ -52,6 +52,9 @@ def _load(name: str = "liboracle.so") -> C.CDLL:
     lib.orc_mean_kernel.argtypes = [_f32p, C.c_int]
     lib.orc_noise_filter.argtypes = [_u8p, _u8p, C.c_int, C.c_int, C.c_int, _f32p]
     lib.orc_text_overlay.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.c_int, C.c_int, C.c_char_p, C.c_char_p]
+    lib.orc_jpeg_info.argtypes = [_u8p, C.c_size_t, _i32p, _i32p, _i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_long)]
+    lib.orc_jpeg_coefficients.argtypes = [_u8p, C.c_size_t, C.POINTER(C.c_int16), C.c_long]
+    lib.orc_jpeg_decode_bgr.argtypes = [_u8p, C.c_size_t, _u8p, C.c_int, C.c_int]
     lib.orc_create.restype = C.c_void_p
     lib.orc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _u8p,
                                _u8p, C.c_int, C.c_int, C.c_char_p]
@@ -217,6 +220,40 @@ def noise_filter(image: np.ndarray, width: int, height: int, K: int, k: np.ndarr
     k = np.ascontiguousarray(k, dtype=np.float32).reshape(-1)
     out = np.empty(img.size, dtype=np.uint8)
     lib().orc_noise_filter(_p8(img), _p8(out), width, height, K, _pf(k))
+    return out
+
+
+def jpeg_info(jpg) -> dict:
+    """Geometry of a baseline JPEG (oracle/jpeg_oracle.c)."""
+    b = np.ascontiguousarray(np.frombuffer(bytes(jpg), dtype=np.uint8))
+    v = [C.c_int() for _ in range(6)]
+    nb = C.c_long()
+    e = lib().orc_jpeg_info(_p8(b), b.size, *[C.byref(x) for x in v], C.byref(nb))
+    if e:
+        raise ValueError(f"jpeg oracle: not a supported baseline JPEG ({e})")
+    return dict(width=v[0].value, height=v[1].value, hs=v[2].value, vs=v[3].value, ncomp=v[4].value,
+                restart_interval=v[5].value, nblocks=nb.value)
+
+
+def jpeg_coefficients(jpg) -> np.ndarray:
+    """Quantised DCT coefficients [nblocks, 64] in scan order, natural order inside a block, DC absolute."""
+    info = jpeg_info(jpg)
+    b = np.ascontiguousarray(np.frombuffer(bytes(jpg), dtype=np.uint8))
+    out = np.zeros((info["nblocks"], 64), dtype=np.int16)
+    e = lib().orc_jpeg_coefficients(_p8(b), b.size, out.ctypes.data_as(C.POINTER(C.c_int16)), info["nblocks"])
+    if e:
+        raise ValueError(f"jpeg oracle: entropy decode failed ({e})")
+    return out
+
+
+def jpeg_decode_bgr(jpg) -> np.ndarray:
+    """What cv2.imread / VideoCapture (libjpeg-turbo defaults) make of a baseline JPEG: [h, w, 3] BGR."""
+    info = jpeg_info(jpg)
+    b = np.ascontiguousarray(np.frombuffer(bytes(jpg), dtype=np.uint8))
+    out = np.zeros((info["height"], info["width"], 3), dtype=np.uint8)
+    e = lib().orc_jpeg_decode_bgr(_p8(b), b.size, _p8(out), info["width"], info["height"])
+    if e:
+        raise ValueError(f"jpeg oracle: decode failed ({e})")
     return out
 
 
