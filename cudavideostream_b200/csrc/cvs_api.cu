@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nvjpeg.h>
+#include <cooperative_groups.h>
 
 #include <atomic>
 #include <cmath>
@@ -20,6 +21,7 @@
 #include <string>
 
 #include "cvs_filter_kernels.cuh"
+#include "cvs_jpeg_host.hpp"
 #include "cvs_stream_kernel.cuh"
 #include "cvs_stream_ws.cuh"
 
@@ -158,6 +160,31 @@ const NvJpegApi *nvjpeg_api()
 
 constexpr int kSlots = 4; // tickets that may be outstanding per stream
 
+// scratch of the GPU JPEG decoder (cvs_jpeg.cuh), one set per handle: decodes of a handle are ordered on one stream
+struct JpegDecoder {
+    uint8_t *d_raw = nullptr, *d_unst = nullptr; // entropy-coded segment as received / unstuffed (zero-padded)
+    size_t raw_cap = 0;
+    uint32_t *d_block_kept = nullptr, *d_total_bits = nullptr;
+    cvs::jpg::Tables *d_tables = nullptr;
+    cvs::jpg::Tables tables_host;  // what d_tables holds
+    bool tables_valid = false;
+    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr;
+    int32_t *d_dcs = nullptr, *d_tile_dc = nullptr;
+    size_t sub_cap = 0;
+    unsigned int *d_changed = nullptr;
+    int16_t *d_coef = nullptr;
+    uint8_t *d_planes = nullptr;
+    size_t block_cap = 0;
+    int coop_blocks_per_sm = 0;
+    uint32_t sub_bits = 1024;
+    void release()
+    {
+        cudaFree(d_raw); cudaFree(d_unst); cudaFree(d_block_kept); cudaFree(d_total_bits); cudaFree(d_tables);
+        cudaFree(d_entry); cudaFree(d_used); cudaFree(d_nblk); cudaFree(d_tile_blk); cudaFree(d_dcs); cudaFree(d_tile_dc);
+        cudaFree(d_changed); cudaFree(d_coef); cudaFree(d_planes);
+    }
+};
+
 struct Slot {
     uint8_t *d_in = nullptr;   // raw frame as uploaded
     int *d_xs = nullptr;
@@ -277,6 +304,8 @@ struct cvs_stream_s {
     unsigned int *h_status = nullptr; // pinned
     unsigned long long *d_desc = nullptr;
     size_t desc_words = 0;
+    JpegDecoder jd;                     // cvs_submit_jpeg / cvs_decode_jpeg_device: the library's own decoder (cvs_jpeg.cuh)
+    int jpeg_decoder = 0;               // 0: own decoder, nvJPEG for streams it does not cover; 1: own only; 2: nvJPEG only
     nvjpegHandle_t jpeg = nullptr;      // cvs_submit_jpeg / cvs_decode_jpeg_device: nvJPEG handle (on first use)
     bool jpeg_batched = false;          // the handle's backend wants the batched entry points (hardware engine / GPU Huffman)
     nvjpegJpegState_t jpeg_state = nullptr; // decoder state of cvs_decode_jpeg_device
@@ -621,6 +650,8 @@ cvs_status status_word(unsigned int w)
 {
     if (w & cvs::kStatusWatchdog) return fail(CVS_ERR_INTERNAL, "device watchdog tripped (status 0x%x)", w);
     if (w & cvs::kStatusCapacity) return fail(CVS_ERR_CAPACITY, "payload capacity exceeded");
+    if (w & (cvs::jpg::kJpegNotConverged | cvs::jpg::kJpegBlockCount))
+        return fail(CVS_ERR_INVALID, "damaged JPEG bitstream (decoder status 0x%x): the frame's payload is not valid", w);
     return CVS_OK;
 }
 
@@ -714,6 +745,11 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     }
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0;
+    if (const char *jd = getenv("CVS_JPEG_DECODER")) h->jpeg_decoder = !strcmp(jd, "own") ? 1 : (!strcmp(jd, "nvjpeg") ? 2 : 0);
+    if (const char *sb = getenv("CVS_JPEG_SUB_BITS")) { // subsequence length of the parallel Huffman decode (measurements)
+        const int v = atoi(sb);
+        if (v >= 64 && v <= 65536 && v % 32 == 0) h->jd.sub_bits = (uint32_t)v;
+    }
     if (const char *pb = getenv("CVS_PUSH_BLOCKS")) h->push_blocks = atoi(pb);
     memset(&h->weights, 0, sizeof h->weights);
     if (cfg->noise_filter) memcpy(h->weights.k, cfg->kweights, sizeof(float) * cfg->ksize * cfg->ksize);
@@ -813,6 +849,7 @@ cvs_status cvs_destroy(cvs_handle h)
     }
     cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
     cudaFree(h->d_band_pos);
+    h->jd.release();
     if (h->jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(h->jpeg_state);
     if (h->jpeg && g_nvjpeg.ok) g_nvjpeg.Destroy(h->jpeg);
     cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
@@ -854,8 +891,8 @@ cvs_status cvs_free_host(void *ptr)
 // common body of cvs_submit / cvs_submit_io (reference-format payload into diff_out / xs / pos) and cvs_submit_wire
 // (wire_out != nullptr: compact "CVW1" frame, see cvs_filter_kernels.cuh)
 // decode one baseline JPEG of the stream's frame size into d_out (BGR interleaved, pitch 3*width), asynchronously on `st`
-static cvs_status jpeg_decode(cvs_handle h, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
-                              cudaStream_t st)
+static cvs_status jpeg_decode_nvjpeg(cvs_handle h, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
+                                     cudaStream_t st)
 {
     const NvJpegApi *nj = nvjpeg_api();
     if (!nj) return fail(CVS_ERR_NODEVICE, "libnvjpeg could not be loaded: %s", dlerror());
@@ -912,6 +949,141 @@ static cvs_status jpeg_decode(cvs_handle h, nvjpegJpegState_t *state, const uint
     return CVS_OK;
 }
 
+// The library's own decoder (cvs_jpeg.cuh): bit for bit the pixels OpenCV / libjpeg-turbo produce.  `status` receives the
+// decoder's status bits (device word, OR-ed).  *unsupported is set when the bitstream is a JPEG this decoder does not
+// cover (restart intervals, progressive, other samplings); nothing has been enqueued then.
+static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out, cudaStream_t st,
+                                  unsigned int *d_status, bool *unsupported)
+{
+    namespace J = cvs::jpg;
+    JpegDecoder &jd = h->jd;
+    *unsupported = false;
+    static thread_local J::Parsed P;
+    const J::ParseStatus ps = J::parse(jpeg, jpeg_bytes, jd.sub_bits, &P);
+    if (ps == J::kParseUnsupported) {
+        *unsupported = true;
+        return CVS_OK;
+    }
+    if (ps != J::kParseOk) return fail(CVS_ERR_INVALID, "not a decodable baseline JPEG");
+    const J::Geometry &g = P.g;
+    if (g.width != h->width || g.height != h->height)
+        return fail(CVS_ERR_INVALID, "JPEG is %dx%d, the stream is %dx%d", g.width, g.height, h->width, h->height);
+
+    // ---- scratch
+    const size_t raw_pad = round_up(P.scan_bytes, 4096) + 4096;
+    if (raw_pad > jd.raw_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(jd.d_raw); cudaFree(jd.d_unst); cudaFree(jd.d_block_kept);
+        jd.d_raw = jd.d_unst = nullptr; jd.d_block_kept = nullptr; jd.raw_cap = 0;
+        const size_t cap = raw_pad + raw_pad / 2;
+        CU_TRY(cudaMalloc(&jd.d_raw, cap));
+        CU_TRY(cudaMalloc(&jd.d_unst, cap));
+        CU_TRY(cudaMalloc(&jd.d_block_kept, (cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)));
+        jd.raw_cap = cap;
+    }
+    if (!jd.d_total_bits) {
+        CU_TRY(cudaMalloc(&jd.d_total_bits, sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_tables, sizeof(J::Tables)));
+        CU_TRY(cudaMalloc(&jd.d_changed, J::kMaxRounds * sizeof(unsigned int)));
+    }
+    const size_t nsub_cap = (jd.raw_cap * 8 + jd.sub_bits - 1) / jd.sub_bits + 1;
+    if (nsub_cap > jd.sub_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(jd.d_entry); cudaFree(jd.d_used); cudaFree(jd.d_nblk); cudaFree(jd.d_tile_blk); cudaFree(jd.d_dcs); cudaFree(jd.d_tile_dc);
+        jd.d_entry = jd.d_used = jd.d_nblk = jd.d_tile_blk = nullptr; jd.d_dcs = jd.d_tile_dc = nullptr; jd.sub_cap = 0;
+        const size_t ntile_cap = nsub_cap / J::kEntropyThreads + 2;
+        CU_TRY(cudaMalloc(&jd.d_entry, (nsub_cap + 2) * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_used, nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_nblk, nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_dcs, 3 * nsub_cap * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&jd.d_tile_blk, ntile_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_tile_dc, 3 * ntile_cap * sizeof(int32_t)));
+        jd.sub_cap = nsub_cap;
+    }
+    const size_t luma_bytes = (size_t)g.mcux * 8 * g.H * g.mcuy * 8 * g.V, chroma_bytes = (size_t)g.mcux * 8 * g.mcuy * 8;
+    if (g.nblocks > jd.block_cap) {
+        CU_TRY(cudaStreamSynchronize(st));
+        cudaFree(jd.d_coef); cudaFree(jd.d_planes);
+        jd.d_coef = nullptr; jd.d_planes = nullptr; jd.block_cap = 0;
+        CU_TRY(cudaMalloc(&jd.d_coef, (size_t)g.nblocks * 64 * sizeof(int16_t)));
+        CU_TRY(cudaMalloc(&jd.d_planes, (size_t)g.nblocks * 64 + 256));
+        jd.block_cap = g.nblocks;
+    }
+    if (!jd.tables_valid || memcmp(&jd.tables_host, &P.t, sizeof(J::Tables)) != 0) {
+        // rare (a camera sends the same tables with every frame); the pageable source is staged before the call returns
+        CU_TRY(cudaMemcpyAsync(jd.d_tables, &P.t, sizeof(J::Tables), cudaMemcpyHostToDevice, st));
+        memcpy(&jd.tables_host, &P.t, sizeof(J::Tables));
+        jd.tables_valid = true;
+    }
+
+    // ---- the entropy-coded segment crosses PCIe (0.4 MB instead of the 6.2 MB frame), FF 00 -> FF
+    const uint32_t raw_len = (uint32_t)P.scan_bytes;
+    CU_TRY(cudaMemcpyAsync(jd.d_raw, jpeg + P.scan_offset, raw_len, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(jd.d_unst, 0, round_up(raw_len, 4096) + 64, st));
+    const uint32_t ublocks = (raw_len + J::kUnstuffThreads * J::kUnstuffBytes - 1) / (J::kUnstuffThreads * J::kUnstuffBytes);
+    J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept);
+    J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_unst, jd.d_total_bits);
+
+    // ---- Huffman decode: one cooperative launch (sync rounds, prefix sums, coefficient write)
+    CU_TRY(cudaMemsetAsync(jd.d_changed, 0, J::kMaxRounds * sizeof(unsigned int), st));
+    CU_TRY(cudaMemsetAsync(jd.d_coef, 0, (size_t)g.nblocks * 64 * sizeof(int16_t), st));
+    if (!jd.coop_blocks_per_sm) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jd.coop_blocks_per_sm, J::k_entropy, J::kEntropyThreads, 0));
+        if (jd.coop_blocks_per_sm < 1) return fail(CVS_ERR_INTERNAL, "k_entropy does not fit an SM");
+    }
+    J::EntropyParams ep;
+    ep.tables = jd.d_tables;
+    ep.g = g;
+    ep.words = reinterpret_cast<const uint32_t *>(jd.d_unst);
+    ep.total_bits = jd.d_total_bits;
+    ep.entry = jd.d_entry;
+    ep.used = jd.d_used;
+    ep.nblk = jd.d_nblk;
+    ep.dcs = jd.d_dcs;
+    ep.tile_blk = jd.d_tile_blk;
+    ep.tile_dc = jd.d_tile_dc;
+    ep.changed = jd.d_changed;
+    ep.coef = jd.d_coef;
+    ep.status = d_status;
+    const uint32_t ntiles = (g.nsub_max + J::kEntropyThreads - 1) / J::kEntropyThreads;
+    const uint32_t egrid = std::max(1u, std::min(ntiles, (uint32_t)(jd.coop_blocks_per_sm * h->sms)));
+    void *eargs[] = {&ep};
+    CU_TRY(cudaLaunchCooperativeKernel((const void *)J::k_entropy, dim3(egrid), dim3(J::kEntropyThreads), eargs, 0, st));
+
+    // ---- IDCT -> planes -> upsampling + colour conversion -> BGR24
+    J::PlaneParams pp;
+    pp.g = g;
+    pp.tables = jd.d_tables;
+    pp.coef = jd.d_coef;
+    pp.y = jd.d_planes;
+    pp.cb = jd.d_planes + luma_bytes;
+    pp.cr = jd.d_planes + luma_bytes + chroma_bytes;
+    J::k_idct<<<(g.nblocks + J::kIdctThreads - 1) / J::kIdctThreads, J::kIdctThreads, 0, st>>>(pp);
+    J::ColourParams cp;
+    cp.g = g;
+    cp.y = pp.y;
+    cp.cb = pp.cb;
+    cp.cr = pp.cr;
+    cp.bgr = d_out;
+    const dim3 cgrid((unsigned)((g.width + 4 * J::kColourThreads - 1) / (4 * J::kColourThreads)), (unsigned)g.height);
+    J::k_colour<<<cgrid, J::kColourThreads, 0, st>>>(cp);
+    CU_TRY(cudaGetLastError());
+    return CVS_OK;
+}
+
+// decode one baseline JPEG of the stream's frame size into d_out (BGR interleaved, pitch 3*width), asynchronously on `st`
+static cvs_status jpeg_decode(cvs_handle h, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
+                              cudaStream_t st, unsigned int *d_status)
+{
+    if (h->jpeg_decoder != 2) {
+        bool unsupported = false;
+        const cvs_status e = jpeg_decode_own(h, jpeg, jpeg_bytes, d_out, st, d_status, &unsupported);
+        if (e || !unsupported) return e;
+        if (h->jpeg_decoder == 1) return fail(CVS_ERR_INVALID, "JPEG form not covered by the built-in decoder (CVS_JPEG_DECODER=own)");
+    }
+    return jpeg_decode_nvjpeg(h, state, jpeg, jpeg_bytes, d_out, st);
+}
+
 static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *diff_out, uint8_t *show, const char *text,
                                 unsigned int *pos, int *xs, uint8_t *wire_out, uint64_t *ticket, size_t jpeg_bytes = 0)
 {
@@ -930,7 +1102,9 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     // H2D (kernels.cu:461) -- of the raw frame, or of the camera's JPEG bitstream, decoded on the device
     CU_TRY(cudaEventRecord(s.ev_h2d0, h->s_h2d));
     if (jpeg_bytes) {
-        st = jpeg_decode(h, &s.jpeg_state, frame, jpeg_bytes, s.d_in, h->s_h2d);
+        // (the ticket's status word is cleared here, in front of the decoder that may raise bits in it)
+        CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), h->s_h2d));
+        st = jpeg_decode(h, &s.jpeg_state, frame, jpeg_bytes, s.d_in, h->s_h2d, s.d_status);
         if (st) return st;
     } else {
         CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
@@ -942,7 +1116,7 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     const size_t cap = round_up(h->N, 4);
     uint8_t *dshow = (h->mode && show) ? s.d_show : nullptr;
     const double th1 = h->trace ? host_us() : 0;
-    CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), h->s_comp));
+    if (!jpeg_bytes) CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), h->s_comp));
     st = run_frames(h, s.d_in, h->Npad, 1, s.d_pos, s.d_xs, s.d_diff, cap, dshow, h->Npad, text, h->s_comp,
                     /*frames_private=*/true, s.d_status);
     if (st) return st;
@@ -1038,7 +1212,11 @@ cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     cvs_status st = check_handle(h);
     if (st) return st;
     if (!jpeg || jpeg_bytes == 0 || !d_out) return fail(CVS_ERR_INVALID, "null argument");
-    return jpeg_decode(h, &h->jpeg_state, jpeg, jpeg_bytes, d_out, (cudaStream_t)cuda_stream);
+    // (status bits of the decoder go to the handle's own status word: cvs_decode_status reads it)
+    st = jpeg_decode(h, &h->jpeg_state, jpeg, jpeg_bytes, d_out, (cudaStream_t)cuda_stream, h->d_status);
+    if (st) return st;
+    CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
+    return CVS_OK;
 }
 
 cvs_status cvs_submit_wire(cvs_handle h, const uint8_t *frame, uint8_t *wire_out, uint8_t *show, const char *text,

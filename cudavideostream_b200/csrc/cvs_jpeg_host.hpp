@@ -1,0 +1,187 @@
+// cvs_jpeg_host.hpp -- host side of the GPU JPEG decode: marker parsing (T.81 Annex B) and the decoder tables.
+// Plain C++ (no CUDA): also compiled by tests/host/jpeg_sim.cpp.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "cvs_jpeg.cuh"
+
+namespace cvs {
+namespace jpg {
+
+struct Parsed {
+    Geometry g;
+    Tables t;
+    size_t scan_offset = 0; // first byte of the entropy-coded segment
+    size_t scan_bytes = 0;  // up to (not including) the EOI marker
+};
+
+enum ParseStatus {
+    kParseOk = 0,
+    kParseNotJpeg = 1,     // not a JPEG / truncated / inconsistent
+    kParseUnsupported = 2, // a JPEG, but not the form this decoder covers (progressive, restart intervals, other samplings ...)
+};
+
+static const uint8_t kZigzagNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// bits[1..16] = codes per length, vals = symbols in code order  ->  look-ahead table + canonical slow path
+inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, HuffDev *h)
+{
+    memset(h, 0, sizeof *h);
+    memcpy(h->vals, vals, (size_t)nvals);
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+        h->valoff[l] = k - code;
+        if (bits[l]) {
+            if (code + bits[l] > (1 << l)) return false; // over-subscribed
+            if (l <= kLutBits) {
+                for (int c = 0; c < bits[l]; c++) {
+                    const int first = (code + c) << (kLutBits - l);
+                    for (int f = 0; f < (1 << (kLutBits - l)); f++) h->lut[first + f] = (uint16_t)((l << 8) | vals[k + c]);
+                }
+            }
+            code += bits[l];
+            k += bits[l];
+            h->maxcode[l] = code - 1;
+        } else {
+            h->maxcode[l] = -1;
+        }
+        code <<= 1;
+    }
+    h->maxcode[0] = -1;
+    return k == nvals;
+}
+
+inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *out)
+{
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return kParseNotJpeg;
+    struct RawHuff {
+        uint8_t bits[17];
+        uint8_t vals[256];
+        int nvals;
+        bool present;
+    } huff[2][4];
+    uint16_t q[4][64];
+    bool qpresent[4] = {false, false, false, false};
+    memset(huff, 0, sizeof huff);
+    int width = 0, height = 0, ncomp = 0, hs[3] = {0, 0, 0}, vs[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    bool sof = false, sos = false;
+    size_t i = 2;
+    while (i + 4 <= n) {
+        if (d[i] != 0xFF) return kParseNotJpeg;
+        while (i < n && d[i] == 0xFF) i++;
+        if (i >= n) return kParseNotJpeg;
+        const int m = d[i++];
+        if (m == 0xD8 || m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0xD9) return kParseNotJpeg;
+        if (i + 2 > n) return kParseNotJpeg;
+        const size_t L = ((size_t)d[i] << 8) | d[i + 1];
+        if (L < 2 || i + L > n) return kParseNotJpeg;
+        const uint8_t *p = d + i + 2;
+        const size_t pl = L - 2;
+        if (m == 0xDB) {
+            size_t o = 0;
+            while (o < pl) {
+                const int pq = p[o] >> 4, t = p[o] & 15;
+                o++;
+                if (t > 3 || o + (pq ? 128u : 64u) > pl) return kParseNotJpeg;
+                for (int k = 0; k < 64; k++) {
+                    q[t][k] = pq ? (uint16_t)((p[o] << 8) | p[o + 1]) : p[o];
+                    o += pq ? 2 : 1;
+                }
+                qpresent[t] = true;
+            }
+        } else if (m == 0xC4) {
+            size_t o = 0;
+            while (o < pl) {
+                if (o + 17 > pl) return kParseNotJpeg;
+                const int tc = p[o] >> 4, th = p[o] & 15;
+                if (tc > 1 || th > 3) return kParseNotJpeg;
+                RawHuff &h = huff[tc][th];
+                int cnt = 0;
+                h.bits[0] = 0;
+                for (int l = 1; l <= 16; l++) {
+                    h.bits[l] = p[o + l];
+                    cnt += p[o + l];
+                }
+                o += 17;
+                if (cnt > 256 || o + (size_t)cnt > pl) return kParseNotJpeg;
+                memcpy(h.vals, p + o, (size_t)cnt);
+                h.nvals = cnt;
+                h.present = true;
+                o += (size_t)cnt;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {
+            if (pl < 6) return kParseNotJpeg;
+            if (p[0] != 8) return kParseUnsupported;
+            height = (p[1] << 8) | p[2];
+            width = (p[3] << 8) | p[4];
+            ncomp = p[5];
+            if (ncomp != 3 && ncomp != 1) return kParseUnsupported;
+            if (pl < 6 + 3 * (size_t)ncomp) return kParseNotJpeg;
+            for (int c = 0; c < ncomp; c++) {
+                hs[c] = p[7 + 3 * c] >> 4;
+                vs[c] = p[7 + 3 * c] & 15;
+                tq[c] = p[8 + 3 * c];
+                if (tq[c] > 3) return kParseNotJpeg;
+            }
+            sof = true;
+        } else if (m >= 0xC2 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return kParseUnsupported; // progressive, lossless, arithmetic coding
+        } else if (m == 0xDD) {
+            if (pl < 2) return kParseNotJpeg;
+            if ((p[0] << 8) | p[1]) return kParseUnsupported; // restart intervals: independent segments, another decoder's job
+        } else if (m == 0xDA) {
+            if (!sof || pl < 1 || p[0] != ncomp || pl < 1 + 2 * (size_t)ncomp + 3) return sof ? kParseUnsupported : kParseNotJpeg;
+            for (int c = 0; c < ncomp; c++) {
+                td[c] = p[2 + 2 * c] >> 4;
+                ta[c] = p[2 + 2 * c] & 15;
+                if (td[c] > 3 || ta[c] > 3) return kParseNotJpeg;
+            }
+            out->scan_offset = i + L;
+            sos = true;
+            break;
+        }
+        i += L;
+    }
+    if (!sos || width <= 0 || height <= 0) return kParseNotJpeg;
+    if (ncomp == 3) {
+        if (hs[1] != 1 || vs[1] != 1 || hs[2] != 1 || vs[2] != 1) return kParseUnsupported;
+        if (!((hs[0] == 1 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 1) || (hs[0] == 2 && vs[0] == 2))) return kParseUnsupported;
+    } else {
+        hs[0] = vs[0] = 1;
+    }
+    // the entropy-coded segment ends at the EOI marker: the last FF D9 of the buffer (cameras pad behind it at most)
+    size_t end = n;
+    while (end >= out->scan_offset + 2 && !(d[end - 2] == 0xFF && d[end - 1] == 0xD9)) end--;
+    if (end < out->scan_offset + 2) return kParseNotJpeg;
+    out->scan_bytes = end - 2 - out->scan_offset;
+    if (out->scan_bytes == 0 || out->scan_bytes > 0x1fffffffu) return kParseNotJpeg;
+
+    Geometry &g = out->g;
+    g.width = width;
+    g.height = height;
+    g.H = hs[0];
+    g.V = vs[0];
+    g.ncomp = ncomp;
+    g.bpm = hs[0] * vs[0] + (ncomp == 3 ? 2 : 0);
+    g.mcux = (width + 8 * g.H - 1) / (8 * g.H);
+    g.mcuy = (height + 8 * g.V - 1) / (8 * g.V);
+    g.nblocks = (uint32_t)g.mcux * (uint32_t)g.mcuy * (uint32_t)g.bpm;
+    g.sub_bits = sub_bits;
+    g.nsub_max = (uint32_t)((out->scan_bytes * 8 + sub_bits - 1) / sub_bits);
+    memset(&out->t, 0, sizeof out->t);
+    for (int c = 0; c < ncomp; c++) {
+        if (!qpresent[tq[c]] || !huff[0][td[c]].present || !huff[1][ta[c]].present) return kParseNotJpeg;
+        if (!build_huff(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].nvals, &out->t.h[c][0])) return kParseNotJpeg;
+        if (!build_huff(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].nvals, &out->t.h[c][1])) return kParseNotJpeg;
+        for (int k = 0; k < 64; k++) out->t.q[c][kZigzagNatural[k]] = q[tq[c]][k];
+    }
+    return kParseOk;
+}
+
+} // namespace jpg
+} // namespace cvs

@@ -1,0 +1,58 @@
+"""The GPU JPEG decoder's entropy stage, executed on the CPU: tests/host/jpeg_sim.cpp compiles the very same
+__host__ __device__ token functions and table builder as the CUDA kernels (cudavideostream_b200/csrc/cvs_jpeg.cuh,
+cvs_jpeg_host.hpp) with plain g++ and runs k_entropy's round structure sequentially -- guessed entry states, exit states
+handed to the successor, re-decode until nothing changes, prefix sums, write pass.  Its coefficients must equal the
+sequential decode of the oracle (oracle/jpeg_oracle.c: jdhuff.c's decode_mcu) for every subsequence length."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def sim(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("jpeg_sim") / "jpeg_sim")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "host", "jpeg_sim.cpp")])
+    return exe
+
+
+def _run(sim, jpg_path, sub_bits, tmp_path):
+    out = str(tmp_path / "coef.bin")
+    r = subprocess.run([sim, jpg_path, str(sub_bits), out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    return r.returncode, r.stdout.decode(), out
+
+
+@pytest.mark.parametrize("sub_bits", [64, 1024, 8192])
+def test_parallel_entropy_decode_of_a_camera_frame_equals_the_sequential_one(sim, oracle, tmp_path, sub_bits):
+    path = os.path.join(GOLDEN, "k1_f1.jpg")
+    rc, log, out = _run(sim, path, sub_bits, tmp_path)
+    assert rc == 0, log
+    with open(path, "rb") as f:
+        ref = oracle.jpeg_coefficients(f.read())
+    got = np.fromfile(out, dtype=np.int16).reshape(-1, 64)
+    assert got.shape == ref.shape == (120 * 68 * 6, 64)
+    assert np.array_equal(got, ref)
+    # the rounds until no state changes stay far below the number of subsequences (self-synchronisation works)
+    rounds = int(log.strip().splitlines()[-1].split()[1])
+    nsub = int(log.strip().splitlines()[-1].split()[3])
+    assert rounds < max(16, nsub // 20), log.strip().splitlines()[-1]
+
+
+def test_other_samplings_and_sizes(sim, oracle, tmp_path):
+    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    for n in sorted({k.split("/")[0] for k in z.files}):
+        jp = str(tmp_path / (n + ".jpg"))
+        z[n + "/jpg"].tofile(jp)
+        for sub_bits in (32, 96, 1024):
+            rc, log, out = _run(sim, jp, sub_bits, tmp_path)
+            if "_rst" in n:
+                assert rc == 3, f"{n}: restart intervals are reported as unsupported ({log})"
+                continue
+            assert rc == 0, f"{n} S={sub_bits}: {log}"
+            ref = oracle.jpeg_coefficients(z[n + "/jpg"].tobytes())
+            got = np.fromfile(out, dtype=np.int16).reshape(-1, 64)
+            assert np.array_equal(got, ref), f"{n} S={sub_bits}"
