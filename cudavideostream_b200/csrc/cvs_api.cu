@@ -168,7 +168,11 @@ struct JpegDecoder {
     cvs::jpg::Tables *d_tables = nullptr;
     cvs::jpg::Tables tables_host;  // what d_tables holds
     bool tables_valid = false;
-    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr;
+    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr;
+    uint8_t *d_hmap = nullptr;
+    uint32_t *d_mid_state = nullptr, *d_mid_nblk = nullptr;
+    int32_t *d_mid_dc = nullptr;
+    bool hypotheses = true; // CVS_JPEG_HYPOTHESES=0: plain synchronisation rounds (measurements)
     int32_t *d_dcs = nullptr, *d_tile_dc = nullptr;
     size_t sub_cap = 0;
     unsigned int *d_changed = nullptr;
@@ -182,6 +186,7 @@ struct JpegDecoder {
         cudaFree(d_raw); cudaFree(d_unst); cudaFree(d_block_kept); cudaFree(d_total_bits); cudaFree(d_tables);
         cudaFree(d_entry); cudaFree(d_used); cudaFree(d_nblk); cudaFree(d_tile_blk); cudaFree(d_dcs); cudaFree(d_tile_dc);
         cudaFree(d_changed); cudaFree(d_coef); cudaFree(d_planes);
+        cudaFree(d_hx); cudaFree(d_hy); cudaFree(d_hmap); cudaFree(d_mid_state); cudaFree(d_mid_nblk); cudaFree(d_mid_dc);
     }
 };
 
@@ -746,6 +751,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0;
     if (const char *jd = getenv("CVS_JPEG_DECODER")) h->jpeg_decoder = !strcmp(jd, "own") ? 1 : (!strcmp(jd, "nvjpeg") ? 2 : 0);
+    if (const char *hy = getenv("CVS_JPEG_HYPOTHESES")) h->jd.hypotheses = atoi(hy) != 0;
     if (const char *sb = getenv("CVS_JPEG_SUB_BITS")) { // subsequence length of the parallel Huffman decode (measurements)
         const int v = atoi(sb);
         if (v >= 64 && v <= 65536 && v % 32 == 0) h->jd.sub_bits = (uint32_t)v;
@@ -990,7 +996,10 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     if (nsub_cap > jd.sub_cap) {
         CU_TRY(cudaStreamSynchronize(st));
         cudaFree(jd.d_entry); cudaFree(jd.d_used); cudaFree(jd.d_nblk); cudaFree(jd.d_tile_blk); cudaFree(jd.d_dcs); cudaFree(jd.d_tile_dc);
-        jd.d_entry = jd.d_used = jd.d_nblk = jd.d_tile_blk = nullptr; jd.d_dcs = jd.d_tile_dc = nullptr; jd.sub_cap = 0;
+        cudaFree(jd.d_hx); cudaFree(jd.d_hy); cudaFree(jd.d_hmap); cudaFree(jd.d_mid_state); cudaFree(jd.d_mid_nblk); cudaFree(jd.d_mid_dc);
+        jd.d_mid_state = jd.d_mid_nblk = nullptr; jd.d_mid_dc = nullptr;
+        jd.d_entry = jd.d_used = jd.d_nblk = jd.d_tile_blk = jd.d_hx = jd.d_hy = nullptr; jd.d_dcs = jd.d_tile_dc = nullptr;
+        jd.d_hmap = nullptr; jd.sub_cap = 0;
         const size_t ntile_cap = nsub_cap / J::kEntropyThreads + 2;
         CU_TRY(cudaMalloc(&jd.d_entry, (nsub_cap + 2) * sizeof(uint32_t)));
         CU_TRY(cudaMalloc(&jd.d_used, nsub_cap * sizeof(uint32_t)));
@@ -998,6 +1007,12 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
         CU_TRY(cudaMalloc(&jd.d_dcs, 3 * nsub_cap * sizeof(int32_t)));
         CU_TRY(cudaMalloc(&jd.d_tile_blk, ntile_cap * sizeof(uint32_t)));
         CU_TRY(cudaMalloc(&jd.d_tile_dc, 3 * ntile_cap * sizeof(int32_t)));
+        CU_TRY(cudaMalloc(&jd.d_hx, 6 * nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_hy, 6 * nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_hmap, 16 * nsub_cap));
+        CU_TRY(cudaMalloc(&jd.d_mid_state, J::kMaxSplit * nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_mid_nblk, J::kMaxSplit * nsub_cap * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&jd.d_mid_dc, 3 * J::kMaxSplit * nsub_cap * sizeof(int32_t)));
         jd.sub_cap = nsub_cap;
     }
     const size_t luma_bytes = (size_t)g.mcux * 8 * g.H * g.mcuy * 8 * g.V, chroma_bytes = (size_t)g.mcux * 8 * g.mcuy * 8;
@@ -1026,6 +1041,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
 
     // ---- Huffman decode: one cooperative launch (sync rounds, prefix sums, coefficient write)
     CU_TRY(cudaMemsetAsync(jd.d_changed, 0, J::kMaxRounds * sizeof(unsigned int), st));
+    CU_TRY(cudaMemsetAsync(jd.d_entry, 0, ((size_t)g.nsub_max + 2) * sizeof(uint32_t), st)); // first guess: a block starts here
     CU_TRY(cudaMemsetAsync(jd.d_coef, 0, (size_t)g.nblocks * 64 * sizeof(int16_t), st));
     if (!jd.coop_blocks_per_sm) {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jd.coop_blocks_per_sm, J::k_entropy, J::kEntropyThreads, 0));
@@ -1042,10 +1058,23 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     ep.dcs = jd.d_dcs;
     ep.tile_blk = jd.d_tile_blk;
     ep.tile_dc = jd.d_tile_dc;
+    // the write pass runs with one thread per G bits: S/8 or S/4 when that is a multiple of 32 bits
+    ep.mid.nsplit = jd.sub_bits % 256 == 0 ? 8u : (jd.sub_bits % 128 == 0 ? 4u : 1u);
+    ep.mid.G = jd.sub_bits / ep.mid.nsplit;
+    ep.mid.stride = ep.mid.nsplit * g.nsub_max;
+    ep.mid.state = jd.d_mid_state;
+    ep.mid.nblk = jd.d_mid_nblk;
+    ep.mid.dc = jd.d_mid_dc;
+    ep.hx = jd.d_hx;
+    ep.hy = jd.d_hy;
+    ep.hmap = jd.d_hmap;
+    ep.hypotheses = jd.hypotheses ? 1u : 0u;
     ep.changed = jd.d_changed;
     ep.coef = jd.d_coef;
     ep.status = d_status;
-    const uint32_t ntiles = (g.nsub_max + J::kEntropyThreads - 1) / J::kEntropyThreads;
+    ep.debug = getenv("CVS_JPEG_TRACE") ? (uint32_t)atoi(getenv("CVS_JPEG_TRACE")) : 0u;
+    // one thread per subsequence and phase hypothesis in the first phases, one per subsequence afterwards
+    const uint32_t ntiles = (g.nsub_max * (jd.hypotheses ? (uint32_t)g.bpm : 1u) + J::kEntropyThreads - 1) / J::kEntropyThreads;
     const uint32_t egrid = std::max(1u, std::min(ntiles, (uint32_t)(jd.coop_blocks_per_sm * h->sms)));
     void *eargs[] = {&ep};
     CU_TRY(cudaLaunchCooperativeKernel((const void *)J::k_entropy, dim3(egrid), dim3(J::kEntropyThreads), eargs, 0, st));

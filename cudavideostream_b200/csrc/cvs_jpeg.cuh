@@ -26,6 +26,7 @@
 // synchronisation logic on the CPU (g++, no GPU).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CVS_HD __host__ __device__ __forceinline__
@@ -36,21 +37,72 @@
 namespace cvs {
 namespace jpg {
 
-constexpr int kLutBits = 9;
-constexpr int kMaxRounds = 4096; // sync rounds before the decode is declared failed (a real frame needs < 10)
+constexpr int kLutBits = 9;      // first-level look-ahead
+constexpr int kLut2Bits = 7;     // second level: the remaining bits of a 16-bit code
+constexpr int kLut2Tables = 8;   // second-level tables per Huffman table (the standard tables need 5)
+constexpr int kMaxSplit = 8;     // write-pass threads per subsequence
+constexpr int kMaxRounds = 4096; // rounds before the decode is declared failed (a camera frame needs one)
 
-// canonical Huffman table as the decoder wants it: kLutBits of look-ahead resolve every code of that length or shorter
-// (entry = length << 8 | symbol; 0: longer code, walk maxcode[] as jdhuff.c's slow path does)
+// Canonical Huffman table as the decoder wants it.  A decoded token is one 32-bit entry:
+//   bits 0-7 symbol (run << 4 | size), 8-12 code length, 13-18 token length (code + size bits),
+//   19-25 advance of the zig-zag position (DC: 1; coefficient: run + 1; ZRL: 16; EOB: 64 = to the end of the block)
+// lut[first kLutBits bits] resolves every code of that length or shorter; for a longer code it holds kEntryLevel2 | t and
+// lut2[t][next kLut2Bits bits] resolves it; when a table has more than kLut2Tables long prefixes the entry is
+// kEntrySlow and maxcode[] is walked as jdhuff.c's slow path does.  Codes that do not exist decode as a zero symbol of
+// 16 bits (damaged data; libjpeg warns and uses zero as well).
+constexpr uint32_t kEntryLevel2 = 0x80000000u, kEntrySlow = 0x40000000u;
 struct HuffDev {
-    uint16_t lut[1 << kLutBits];
+    uint32_t lut[1 << kLutBits];
+    uint32_t lut2[kLut2Tables][1 << kLut2Bits];
     int32_t maxcode[17]; // largest code of length l (1..16), -1: none
     int32_t valoff[17];  // valptr[l] - mincode[l]
     uint8_t vals[256];
+    uint32_t is_ac;
 };
+constexpr uint32_t kOffLut2 = sizeof(uint32_t) << kLutBits;
+constexpr uint32_t kOffMaxcode = kOffLut2 + sizeof(uint32_t) * kLut2Tables * (1u << kLut2Bits);
+constexpr uint32_t kOffValoff = kOffMaxcode + 17 * 4, kOffVals = kOffValoff + 17 * 4, kOffIsAc = kOffVals + 256;
+static_assert(sizeof(HuffDev) == kOffIsAc + 4, "HuffDev is addressed by byte offsets");
+
+CVS_HD uint32_t make_entry(uint32_t sym, uint32_t len, uint32_t is_ac)
+{
+    const uint32_t s = sym & 15u, run = sym >> 4;
+    const uint32_t kadd = is_ac ? (s ? run + 1u : (run == 15u ? 16u : 64u)) : 1u;
+    return sym | (len << 8) | ((len + s) << 13) | (kadd << 19);
+}
 
 struct Tables {
     HuffDev h[3][2];   // per component: [0] DC table, [1] AC table
     uint16_t q[3][64]; // per component: quantisation table in natural (row-major) order
+};
+
+// The tables as the token loop reads them: byte offsets from the start of a Tables object -- in shared memory on the
+// device (explicit ld.shared: no generic-address arithmetic inside the loop), plain memory in the host build.
+struct TableRef {
+#if defined(__CUDA_ARCH__)
+    uint32_t base;
+    __device__ __forceinline__ uint32_t ld32(uint32_t off) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + off));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld8(uint32_t off) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(base + off));
+        return v;
+    }
+#else
+    const uint8_t *base;
+    uint32_t ld32(uint32_t off) const
+    {
+        uint32_t v;
+        memcpy(&v, base + off, 4);
+        return v;
+    }
+    uint32_t ld8(uint32_t off) const { return base[off]; }
+#endif
 };
 
 struct Geometry {
@@ -67,12 +119,13 @@ struct Geometry {
 // ---- entry / exit state of a subsequence, packed: bit offset of the first own token (0..31) | phase << 5 | k << 8 -------
 CVS_HD uint32_t pack_state(uint32_t off, uint32_t ph, uint32_t k) { return off | (ph << 5) | (k << 8); }
 constexpr uint32_t kStateUnset = 0xffffffffu;
+constexpr uint32_t kNoCandidate = 15u;
 
 // what one run over a subsequence leaves behind
 struct RunResult {
     uint32_t exit_state;
-    uint32_t nblocks; // blocks completed by tokens that start in this subsequence
-    int32_t dcsum[3]; // DC differences decoded in this subsequence, per component
+    uint32_t nblocks;           // blocks completed by tokens that start in this subsequence
+    int32_t dc0, dc1, dc2;      // DC differences decoded in this subsequence, per component
 };
 
 CVS_HD uint32_t bswap32(uint32_t x)
@@ -84,116 +137,158 @@ CVS_HD uint32_t bswap32(uint32_t x)
 #endif
 }
 
-// 32 bits of the unstuffed string starting at bit p (big-endian bit order), through a two-word register window
+CVS_HD TableRef table_ref(const Tables *t) // device: t lives in shared memory
+{
+    TableRef r;
+#if defined(__CUDA_ARCH__)
+    r.base = (uint32_t)__cvta_generic_to_shared(t);
+#else
+    r.base = reinterpret_cast<const uint8_t *>(t);
+#endif
+    return r;
+}
+
+// 32 bits of the unstuffed string starting at bit p (big-endian bit order).  Held: the two words under the window, the
+// one behind them, and the one behind that as it was loaded an iteration (or more) ago -- every call issues the load of
+// word (p >> 5) + 3 and nobody reads its result before a later call, so a warp (which issues in order and waits at the
+// first instruction that reads a loaded register) never waits for memory on the token chain.
+// p may advance by at most 31 bits between two calls (a token is at most 16 + 15 bits long).
 struct BitWindow {
     const uint32_t *words;
-    uint32_t widx, hi, lo;
+    uint32_t widx, hi, lo, n1, q; // n1 = word widx + 2 (as loaded), q = word widx + 3 (as loaded, possibly still in flight)
     CVS_HD void init(const uint32_t *w, uint32_t p)
     {
         words = w;
         widx = p >> 5;
         hi = bswap32(words[widx]);
         lo = bswap32(words[widx + 1]);
+        n1 = words[widx + 2];
+        q = words[widx + 3];
     }
     CVS_HD uint32_t peek(uint32_t p)
     {
         const uint32_t wi = p >> 5;
-        if (wi != widx) {
-            hi = (wi == widx + 1) ? lo : bswap32(words[wi]);
-            lo = bswap32(words[wi + 1]);
-            widx = wi;
-        }
+        const bool adv = wi != widx;
+        hi = adv ? lo : hi;
+        lo = adv ? bswap32(n1) : lo;
+        n1 = adv ? q : n1;
+        widx = wi;
+        q = words[wi + 3];
         const uint32_t s = p & 31u;
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_l(lo, hi, s);
+#else
         return s ? ((hi << s) | (lo >> (32u - s))) : hi;
+#endif
     }
 };
 
-// jdhuff.c HUFF_EXTEND
-CVS_HD int32_t huff_extend(uint32_t x, uint32_t s) { return x < (1u << (s - 1)) ? (int32_t)x - (int32_t)((1u << s) - 1u) : (int32_t)x; }
-
-CVS_HD void huff_decode(const HuffDev &h, uint32_t w, uint32_t &len, uint32_t &sym)
+// the token at the top of w (see HuffDev); toff = byte offset of the Huffman table
+CVS_HD uint32_t huff_decode(const TableRef &tb, uint32_t toff, uint32_t w)
 {
-    const uint32_t e = h.lut[w >> (32 - kLutBits)];
-    if (e) {
-        len = e >> 8;
-        sym = e & 255u;
-        return;
-    }
-    for (uint32_t l = kLutBits + 1; l <= 16; l++) {
-        const int32_t code = (int32_t)(w >> (32u - l));
-        if (code <= h.maxcode[l]) {
-            len = l;
-            sym = h.vals[(uint32_t)(code + h.valoff[l]) & 255u];
-            return;
-        }
-    }
-    len = 16; // corrupt data: no such code (libjpeg warns and uses a zero symbol)
-    sym = 0;
-}
-
-// One run over subsequence i: tokens that start in [i*S + off, min((i+1)*S, T)).  WRITE: store the coefficients
-// (scan order, natural order inside a block, DC absolute) of blocks first_block.. with the predictors pred[].
-template <bool WRITE>
-CVS_HD RunResult run_subsequence(const Tables &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t i,
-                                 uint32_t entry, const uint8_t *natural, int16_t *coef, uint32_t first_block, int32_t pred0,
-                                 int32_t pred1, int32_t pred2)
-{
-    RunResult r;
-    r.nblocks = 0;
-    r.dcsum[0] = r.dcsum[1] = r.dcsum[2] = 0;
-    const uint32_t S = g.sub_bits;
-    const uint32_t begin = i * S, end_nominal = begin + S;
-    const uint32_t end = end_nominal < total_bits ? end_nominal : total_bits;
-    uint32_t p = begin + (entry & 31u), ph = (entry >> 5) & 7u, k = (entry >> 8) & 63u;
-    int32_t pred[3] = {pred0, pred1, pred2};
-    uint32_t blk = first_block;
-    const uint32_t nluma = (uint32_t)(g.bpm - (g.ncomp == 3 ? 2 : 0));
-    if (begin < total_bits) {
-        BitWindow bw;
-        bw.init(words, p);
-        while (p < end) {
-            const uint32_t c = ph < nluma ? 0u : ph - nluma + 1u;
-            const uint32_t w = bw.peek(p);
-            uint32_t len, sym;
-            if (k == 0) {
-                huff_decode(tb.h[c][0], w, len, sym);
-                const uint32_t s = sym & 15u;
-                int32_t v = 0;
-                if (s) v = huff_extend((w << len) >> (32u - s), s);
-                p += len + s;
-                if (WRITE) {
-                    pred[c] += v;
-                    if (blk < g.nblocks) coef[(size_t)blk * 64] = (int16_t)pred[c];
-                } else {
-                    r.dcsum[c] += v;
-                }
-                k = 1;
-            } else {
-                huff_decode(tb.h[c][1], w, len, sym);
-                const uint32_t run = sym >> 4, s = sym & 15u;
-                if (s) {
-                    k += run;
-                    if (WRITE) {
-                        const int32_t v = huff_extend((w << len) >> (32u - s), s);
-                        if (k < 64 && blk < g.nblocks) coef[(size_t)blk * 64 + natural[k]] = (int16_t)v;
-                    }
-                    p += len + s;
-                    k++;
-                } else {
-                    p += len;
-                    k = run == 15 ? k + 16 : 64;
-                }
-                if (k >= 64) {
-                    k = 0;
-                    ph = ph + 1 == (uint32_t)g.bpm ? 0u : ph + 1;
-                    blk++;
-                    r.nblocks++;
+    uint32_t e = tb.ld32(toff + 4u * (w >> (32 - kLutBits)));
+    if (e >> 30) {
+        if (e & kEntryLevel2) {
+            e = tb.ld32(toff + kOffLut2 + ((e & 0xffu) << (kLut2Bits + 2)) + 4u * ((w >> (32 - kLutBits - kLut2Bits)) & ((1u << kLut2Bits) - 1u)));
+        } else { // a table with more long prefixes than second-level tables: canonical search (jdhuff.c slow path)
+            const uint32_t is_ac = tb.ld32(toff + kOffIsAc);
+            e = make_entry(0, 16, is_ac);
+            for (uint32_t l = kLutBits + 1; l <= 16; l++) {
+                const int32_t code = (int32_t)(w >> (32u - l));
+                if (code <= (int32_t)tb.ld32(toff + kOffMaxcode + 4u * l)) {
+                    e = make_entry(tb.ld8(toff + kOffVals + ((uint32_t)(code + (int32_t)tb.ld32(toff + kOffValoff + 4u * l)) & 255u)), l, is_ac);
+                    break;
                 }
             }
         }
     }
+    return e;
+}
+
+// Where a counting run leaves the state it passes the inner boundaries of its subsequence in (every G bits), together
+// with the blocks completed and the DC differences summed since the start of the subsequence: the write pass then runs
+// with one thread per G bits instead of one per S bits.
+struct MidRecords {
+    uint32_t *state; // [nsplit * nsub]; kStateUnset: no token starts behind this boundary
+    uint32_t *nblk;
+    int32_t *dc;     // [3][stride]
+    uint32_t stride; // nsplit * nsub_max
+    uint32_t nsplit, G;
+};
+
+// One run over subsequence i: tokens that start in [i*S + off, min((i+1)*S, T)).  WRITE: store the coefficients
+// (scan order, natural order inside a block, DC absolute) of blocks first_block.. with the predictors pred0..2.
+// The token step is one code path for DC and AC tokens, written with selects: the lanes of a warp sit in different places
+// of different blocks, divergent paths would put their latencies in series, and the chain p -> window -> table -> p is
+// what the whole decode waits for.
+template <bool WRITE, bool RECORD = false>
+CVS_HD RunResult run_subsequence(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t i,
+                                 uint32_t entry, const uint8_t *natural, int16_t *coef, uint32_t first_block, int32_t pred0,
+                                 int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
+{
+    RunResult r;
+    int32_t dc0 = pred0, dc1 = pred1, dc2 = pred2;
+    const uint32_t S = g.sub_bits;
+    const uint32_t begin = i * S, end_nominal = begin + S;
+    const uint32_t end = end_nominal < total_bits ? end_nominal : total_bits;
+    uint32_t p = begin + (entry & 31u), ph = (entry >> 5) & 7u, k = (entry >> 8) & 63u;
+    uint32_t blk = first_block, nblocks = 0;
+    const uint32_t nluma = (uint32_t)(g.bpm - (g.ncomp == 3 ? 2 : 0)), bpm = (uint32_t)g.bpm;
+    uint32_t next_inner = 0, inner = 1;
+    if (RECORD) {
+        next_inner = begin + mid->G;
+        for (uint32_t j = 1; j < mid->nsplit; j++) mid->state[i * mid->nsplit + j] = kStateUnset;
+    }
+    if (begin < total_bits && p < end) {
+        BitWindow bw;
+        bw.init(words, p);
+        do {
+            const uint32_t is_ac = k != 0 ? 1u : 0u;
+            const uint32_t c = ph < nluma ? 0u : ph - nluma + 1u;
+            const uint32_t w = bw.peek(p);
+            const uint32_t e = huff_decode(tb, (2u * c + is_ac) * (uint32_t)sizeof(HuffDev), w);
+            const uint32_t len = (e >> 8) & 31u, s = e & 15u;
+            // jdhuff.c HUFF_EXTEND of the s bits behind the code (0 for s = 0)
+            const uint32_t x = ((w << len) >> 1) >> (31u - s);
+            const int32_t v = (int32_t)x + ((((int32_t)x - (int32_t)((1u << s) >> 1)) >> 31) & (int32_t)((0xffffffffu << s) + 1u));
+            p += (e >> 13) & 63u;
+            const int32_t vdc = is_ac ? 0 : v;
+            dc0 += c == 0 ? vdc : 0;
+            dc1 += c == 1 ? vdc : 0;
+            dc2 += c == 2 ? vdc : 0;
+            if (WRITE) {
+                if (blk < g.nblocks) {
+                    const uint32_t kk = k + ((e >> 4) & 15u); // zig-zag position of an AC coefficient
+                    if (!is_ac) coef[(size_t)blk * 64] = (int16_t)(c == 0 ? dc0 : (c == 1 ? dc1 : dc2));
+                    else if (s && kk < 64) coef[(size_t)blk * 64 + natural[kk]] = (int16_t)v;
+                }
+            }
+            k += (e >> 19) & 127u;
+            const bool block_end = k >= 64u;
+            k = block_end ? 0u : k;
+            ph = block_end ? (ph + 1 == bpm ? 0u : ph + 1) : ph;
+            blk += block_end ? 1u : 0u;
+            nblocks += block_end ? 1u : 0u;
+            if (RECORD) {
+                if (p >= next_inner && p < end) { // the first token behind an inner boundary starts at p
+                    const uint32_t idx = i * mid->nsplit + inner;
+                    mid->state[idx] = pack_state(p - next_inner, ph, k);
+                    mid->nblk[idx] = nblocks;
+                    mid->dc[idx] = dc0 - pred0;
+                    mid->dc[mid->stride + idx] = dc1 - pred1;
+                    mid->dc[2 * mid->stride + idx] = dc2 - pred2;
+                    next_inner += mid->G;
+                    inner++;
+                }
+            }
+        } while (p < end);
+    }
     const uint32_t over = p > end_nominal ? p - end_nominal : 0u; // < 32: a token is at most 31 bits long
     r.exit_state = pack_state(over & 31u, ph, k);
+    r.nblocks = nblocks;
+    r.dc0 = WRITE ? dc0 : dc0 - pred0; // sums of the differences when counting
+    r.dc1 = WRITE ? dc1 : dc1 - pred1;
+    r.dc2 = WRITE ? dc2 : dc2 - pred2;
     return r;
 }
 
@@ -203,6 +298,7 @@ CVS_HD RunResult run_subsequence(const Tables &tb, const Geometry &g, const uint
 // =====================================================================================================================
 #if defined(__CUDACC__)
 #include <cooperative_groups.h>
+#include <stdio.h>
 
 namespace cvs {
 namespace jpg {
@@ -322,10 +418,22 @@ struct EntropyParams {
     int32_t *dcs;             // [3][nsub_max] DC sums, then predictors at entry
     uint32_t *tile_blk;       // [ntiles] per-tile totals
     int32_t *tile_dc;         // [3][ntiles]
+    MidRecords mid;           // inner-boundary records of the counting runs (write pass granularity)
+    uint32_t *hx, *hy;        // [nsub_max * bpm] exit states of the phase hypotheses: fresh / followed one subsequence further
+    uint8_t *hmap;            // [nsub_max][16] successor of candidate c of boundary i-1 among the candidates of boundary i
+    uint32_t hypotheses;      // 0: plain rounds from the guess "a block starts here" (A/B measurements)
     unsigned int *changed;    // [kMaxRounds] states changed per round
     int16_t *coef;            // [nblocks][64], zeroed
     unsigned int *status;
+    uint32_t debug;           // CVS_JPEG_TRACE=1: block 0 prints the time of every phase (measurements)
 };
+
+__device__ __forceinline__ unsigned long long jpg_now_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams p)
 {
@@ -335,6 +443,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     __shared__ uint32_t s_scan[4][kEntropyThreads / 32];
     __shared__ uint32_t s_tile_base[4];
     __shared__ uint8_t s_nat[64];
+    __shared__ unsigned long long s_compose[kEntropyThreads];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 64) s_nat[tid] = c_natural[tid];
     {
@@ -343,33 +452,139 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         for (uint32_t j = tid; j < sizeof(Tables) / 4; j += kEntropyThreads) dst[j] = src[j];
     }
     __syncthreads();
+    const TableRef tbr = table_ref(&tb);
     const Geometry g = p.g;
     const uint32_t T = *p.total_bits;
     const uint32_t nsub = (T + g.sub_bits - 1) / g.sub_bits; // <= nsub_max
     const uint32_t ntiles = (nsub + kEntropyThreads - 1) / kEntropyThreads;
 
-    // ---- sync rounds
+    const bool trace = p.debug && blockIdx.x == 0 && tid == 0;
+    unsigned long long t_prev = trace ? jpg_now_ns() : 0ull;
+
+    // ---- phase hypotheses (see the header): seed entry[] with the states the true token sequence passes through
+    if (p.hypotheses) {
+        const uint32_t B = (uint32_t)g.bpm, nh = nsub * B, gstride = gridDim.x * kEntropyThreads;
+        const uint32_t first = blockIdx.x * kEntropyThreads + tid;
+        // X: a block of phase h starts at the subsequence boundary
+        for (uint32_t idx = first; idx < nh; idx += gstride) {
+            const uint32_t i = idx / B, h = idx - i * B;
+            p.hx[idx] = run_subsequence<false>(tbr, g, p.words, T, i, pack_state(0, h, 0), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+        }
+        grid.sync();
+        // Y: the X sequences of the subsequence in front, followed through this one
+        for (uint32_t idx = first; idx < nh; idx += gstride) {
+            const uint32_t i = idx / B;
+            uint32_t y = kStateUnset;
+            if (i) y = run_subsequence<false>(tbr, g, p.words, T, i, __ldcg(p.hx + idx - B), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            p.hy[idx] = y;
+        }
+        grid.sync();
+        // W: the Y sequences followed once more; where does each candidate of boundary i-1 arrive among those of boundary i?
+        for (uint32_t idx = first; idx < nh; idx += gstride) {
+            const uint32_t i = idx / B, h = idx - i * B;
+            uint32_t m0 = kNoCandidate, m1 = kNoCandidate;
+            if (i) {
+                const uint32_t y = __ldcg(p.hy + idx);
+                m0 = B + h; // candidate X_h of the boundary in front arrives here as Y_h, or as a fresh sequence it fell in with
+                for (uint32_t h2 = 0; h2 < B; h2++)
+                    if (__ldcg(p.hx + i * B + h2) == y) {
+                        m0 = h2;
+                        break;
+                    }
+                if (i >= 2) {
+                    const uint32_t w = run_subsequence<false>(tbr, g, p.words, T, i, __ldcg(p.hy + idx - B), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+                    for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
+                        if (__ldcg(p.hx + i * B + h2) == w) m1 = h2;
+                    for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
+                        if (__ldcg(p.hy + i * B + h2) == w) m1 = B + h2;
+                }
+            }
+            p.hmap[(size_t)i * 16 + h] = (uint8_t)m0;
+            p.hmap[(size_t)i * 16 + B + h] = (uint8_t)m1;
+        }
+        grid.sync();
+        // follow candidate 0 of boundary 0 (the exact start) through the maps: a scan of map compositions, one block
+        if (blockIdx.x == 0) {
+            unsigned long long *s_f = reinterpret_cast<unsigned long long *>(&s_compose[0]);
+            const uint32_t chunk = (nsub - 1 + kEntropyThreads - 1) / kEntropyThreads; // maps 1 .. nsub-1
+            const uint32_t lo = 1 + tid * chunk, hi = min(lo + chunk, nsub);
+            auto load_map = [&](uint32_t i) -> unsigned long long {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p.hmap + (size_t)i * 16));
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+                unsigned long long m = 0;
+#pragma unroll
+                for (int c = 0; c < 16; c++) m |= (unsigned long long)((wv[c >> 2] >> (8 * (c & 3))) & 15u) << (4 * c);
+                return m;
+            };
+            auto compose = [&](unsigned long long f, unsigned long long m) -> unsigned long long { // first f, then m
+                unsigned long long r = 0;
+#pragma unroll
+                for (int c = 0; c < 12; c++) {
+                    const uint32_t x = (uint32_t)(f >> (4 * c)) & 15u;
+                    const uint32_t y = x >= 12u ? kNoCandidate : (uint32_t)(m >> (4 * x)) & 15u;
+                    r |= (unsigned long long)y << (4 * c);
+                }
+                return r;
+            };
+            const unsigned long long ident = 0xBA9876543210ull;
+            unsigned long long f = ident;
+            for (uint32_t i = lo; i < hi; i++) f = compose(f, load_map(i));
+            s_f[tid] = f;
+            __syncthreads();
+            for (uint32_t d = 1; d < (uint32_t)kEntropyThreads; d <<= 1) { // inclusive scan (Hillis-Steele)
+                unsigned long long a = ident;
+                if (tid >= d) a = s_f[tid - d];
+                __syncthreads();
+                if (tid >= d) s_f[tid] = compose(a, s_f[tid]);
+                __syncthreads();
+            }
+            uint32_t t = tid ? (uint32_t)(s_f[tid - 1]) & 15u : 0u; // candidate the true sequence is at boundary lo - 1
+            if (tid == 0) p.entry[1] = __ldcg(p.hx); // boundary 0: the exact run
+            for (uint32_t i = lo; i < hi; i++) {
+                if (t < 12u) t = p.hmap[(size_t)i * 16 + t];
+                uint32_t st = __ldcg(p.hx + i * B); // no candidate known: any state, the rounds below repair it
+                if (t < B) st = __ldcg(p.hx + i * B + t);
+                else if (t < 2 * B) st = __ldcg(p.hy + i * B + t - B);
+                p.entry[i + 1] = st;
+            }
+        }
+        __threadfence();
+        grid.sync();
+        if (trace) {
+            printf("hypotheses: %llu ns\n", jpg_now_ns() - t_prev);
+            t_prev = jpg_now_ns();
+        }
+    }
+
+    // ---- rounds: decode from the entry state, hand the exit state on, until no state changes (one round when the
+    //      seeds above are all true; any number otherwise)
     bool converged = false;
     for (uint32_t round = 0; round < (uint32_t)kMaxRounds; round++) {
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const uint32_t i = tile * kEntropyThreads + tid;
             if (i >= nsub) continue;
-            uint32_t e = i == 0 ? pack_state(0, 0, 0) : __ldcg(p.entry + i);
-            if (round == 0 && i) e = pack_state(0, 0, 0); // first guess: a block starts here
+            const uint32_t e = i == 0 ? pack_state(0, 0, 0) : __ldcg(p.entry + i);
             if (round && e == p.used[i]) continue;
-            const RunResult r = run_subsequence<false>(tb, g, p.words, T, i, e, s_nat, nullptr, 0, 0, 0, 0);
+            const RunResult r = run_subsequence<false, true>(tbr, g, p.words, T, i, e, s_nat, nullptr, 0, 0, 0, 0, &p.mid);
             p.used[i] = e;
             p.nblk[i] = r.nblocks;
-            p.dcs[i] = r.dcsum[0];
-            p.dcs[g.nsub_max + i] = r.dcsum[1];
-            p.dcs[2 * g.nsub_max + i] = r.dcsum[2];
-            if (round == 0 || __ldcg(p.entry + i + 1) != r.exit_state) {
+            p.dcs[i] = r.dc0;
+            p.dcs[g.nsub_max + i] = r.dc1;
+            p.dcs[2 * g.nsub_max + i] = r.dc2;
+            if (__ldcg(p.entry + i + 1) != r.exit_state) {
                 __stcg(p.entry + i + 1, r.exit_state);
-                if (round && i + 1 < nsub) atomicAdd(p.changed + round, 1u);
+                if (i + 1 < nsub) atomicAdd(p.changed + round, 1u);
             }
         }
+        const unsigned long long t_run = trace ? jpg_now_ns() : 0ull;
         grid.sync();
-        if (round && __ldcg(p.changed + round) == 0) {
+        if (trace) {
+            const unsigned long long t_now = jpg_now_ns();
+            printf("round %u: run %llu ns, barrier %llu ns, %u states changed\n", round, t_run - t_prev, t_now - t_run,
+                   __ldcg(p.changed + round));
+            t_prev = t_now;
+        }
+        if (__ldcg(p.changed + round) == 0) {
             converged = true;
             break;
         }
@@ -456,13 +671,37 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
             base[q] += woff + incl[q] - v[q];
         }
         __syncthreads();
-        // ---- write pass
+        // first block index and DC predictors of the subsequence (over the counts, which are not needed any more)
         if (i < nsub) {
-            const RunResult r = run_subsequence<true>(tb, g, p.words, T, i, p.used[i], s_nat, p.coef, base[0], (int32_t)base[1],
-                                                      (int32_t)base[2], (int32_t)base[3]);
-            if (i == nsub - 1) total_blocks_seen = base[0] + r.nblocks;
+            if (i == nsub - 1) total_blocks_seen = base[0] + v[0];
+            p.nblk[i] = base[0];
+            p.dcs[i] = (int32_t)base[1];
+            p.dcs[g.nsub_max + i] = (int32_t)base[2];
+            p.dcs[2 * g.nsub_max + i] = (int32_t)base[3];
         }
     }
+    grid.sync();
+    // ---- write pass: one thread per G bits, from the states the counting runs left at the inner boundaries
+    {
+        Geometry gw = g;
+        gw.sub_bits = p.mid.G;
+        const uint32_t nsplit = p.mid.nsplit, nparts = nsub * nsplit;
+        for (uint32_t j = blockIdx.x * kEntropyThreads + tid; j < nparts; j += gridDim.x * kEntropyThreads) {
+            const uint32_t i = j / nsplit, part = j - i * nsplit;
+            uint32_t e = __ldcg(p.used + i), blk0 = __ldcg(p.nblk + i);
+            int32_t d0 = __ldcg(p.dcs + i), d1 = __ldcg(p.dcs + g.nsub_max + i), d2 = __ldcg(p.dcs + 2 * g.nsub_max + i);
+            if (part) {
+                e = __ldcg(p.mid.state + j);
+                if (e == kStateUnset) continue;
+                blk0 += __ldcg(p.mid.nblk + j);
+                d0 += __ldcg(p.mid.dc + j);
+                d1 += __ldcg(p.mid.dc + p.mid.stride + j);
+                d2 += __ldcg(p.mid.dc + 2 * p.mid.stride + j);
+            }
+            run_subsequence<true>(tbr, gw, p.words, T, j, e, s_nat, p.coef, blk0, d0, d1, d2);
+        }
+    }
+    if (trace) printf("scan + write: %llu ns\n", jpg_now_ns() - t_prev);
     // the string must hold exactly the image's blocks (padding bits after the last block decode to no complete block
     // in a well-formed stream; more or fewer blocks means a damaged frame)
     if (total_blocks_seen && total_blocks_seen < g.nblocks) atomicOr(p.status, kJpegBlockCount);

@@ -27,20 +27,34 @@ static const uint8_t kZigzagNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 2
                                            41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
                                            30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
 
-// bits[1..16] = codes per length, vals = symbols in code order  ->  look-ahead table + canonical slow path
-inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, HuffDev *h)
+// bits[1..16] = codes per length, vals = symbols in code order  ->  the decoder's tables (see HuffDev)
+inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, uint32_t is_ac, HuffDev *h)
 {
     memset(h, 0, sizeof *h);
     memcpy(h->vals, vals, (size_t)nvals);
-    int code = 0, k = 0;
+    h->is_ac = is_ac;
+    const uint32_t none = make_entry(0, 16, is_ac); // a code that does not exist
+    for (uint32_t &e : h->lut) e = none;
+    for (auto &t : h->lut2)
+        for (uint32_t &e : t) e = none;
+    int code = 0, k = 0, ntab2 = 0;
     for (int l = 1; l <= 16; l++) {
         h->valoff[l] = k - code;
         if (bits[l]) {
             if (code + bits[l] > (1 << l)) return false; // over-subscribed
-            if (l <= kLutBits) {
-                for (int c = 0; c < bits[l]; c++) {
+            for (int c = 0; c < bits[l]; c++) {
+                const uint32_t entry = make_entry(vals[k + c], (uint32_t)l, is_ac);
+                if (l <= kLutBits) {
                     const int first = (code + c) << (kLutBits - l);
-                    for (int f = 0; f < (1 << (kLutBits - l)); f++) h->lut[first + f] = (uint16_t)((l << 8) | vals[k + c]);
+                    for (int f = 0; f < (1 << (kLutBits - l)); f++) h->lut[first + f] = entry;
+                } else {
+                    const int prefix = (code + c) >> (l - kLutBits);
+                    uint32_t &e1 = h->lut[prefix];
+                    if (e1 == none) e1 = ntab2 < kLut2Tables ? (kEntryLevel2 | (uint32_t)ntab2++) : kEntrySlow;
+                    if (e1 & kEntryLevel2) {
+                        const int rest = ((code + c) << (16 - l)) & ((1 << kLut2Bits) - 1);
+                        for (int f = 0; f < (1 << (16 - l)); f++) h->lut2[e1 & 0xff][rest + f] = entry;
+                    } // else: no second-level table left for this prefix, the decoder walks maxcode[]
                 }
             }
             code += bits[l];
@@ -176,8 +190,8 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
     memset(&out->t, 0, sizeof out->t);
     for (int c = 0; c < ncomp; c++) {
         if (!qpresent[tq[c]] || !huff[0][td[c]].present || !huff[1][ta[c]].present) return kParseNotJpeg;
-        if (!build_huff(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].nvals, &out->t.h[c][0])) return kParseNotJpeg;
-        if (!build_huff(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].nvals, &out->t.h[c][1])) return kParseNotJpeg;
+        if (!build_huff(huff[0][td[c]].bits, huff[0][td[c]].vals, huff[0][td[c]].nvals, 0u, &out->t.h[c][0])) return kParseNotJpeg;
+        if (!build_huff(huff[1][ta[c]].bits, huff[1][ta[c]].vals, huff[1][ta[c]].nvals, 1u, &out->t.h[c][1])) return kParseNotJpeg;
         for (int k = 0; k < 64; k++) out->t.q[c][kZigzagNatural[k]] = q[tq[c]][k];
     }
     return kParseOk;

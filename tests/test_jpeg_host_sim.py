@@ -20,16 +20,16 @@ def sim(tmp_path_factory):
     return exe
 
 
-def _run(sim, jpg_path, sub_bits, tmp_path):
+def _run(sim, jpg_path, sub_bits, tmp_path, hypotheses=1):
     out = str(tmp_path / "coef.bin")
-    r = subprocess.run([sim, jpg_path, str(sub_bits), out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    r = subprocess.run([sim, jpg_path, str(sub_bits), out, str(hypotheses)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     return r.returncode, r.stdout.decode(), out
 
 
-@pytest.mark.parametrize("sub_bits", [64, 1024, 8192])
-def test_parallel_entropy_decode_of_a_camera_frame_equals_the_sequential_one(sim, oracle, tmp_path, sub_bits):
+@pytest.mark.parametrize("sub_bits,hypotheses", [(64, 0), (1024, 0), (8192, 0), (256, 1), (1024, 1), (2048, 1)])
+def test_parallel_entropy_decode_of_a_camera_frame_equals_the_sequential_one(sim, oracle, tmp_path, sub_bits, hypotheses):
     path = os.path.join(GOLDEN, "k1_f1.jpg")
-    rc, log, out = _run(sim, path, sub_bits, tmp_path)
+    rc, log, out = _run(sim, path, sub_bits, tmp_path, hypotheses)
     assert rc == 0, log
     with open(path, "rb") as f:
         ref = oracle.jpeg_coefficients(f.read())
@@ -40,6 +40,9 @@ def test_parallel_entropy_decode_of_a_camera_frame_equals_the_sequential_one(sim
     rounds = int(log.strip().splitlines()[-1].split()[1])
     nsub = int(log.strip().splitlines()[-1].split()[3])
     assert rounds < max(16, nsub // 20), log.strip().splitlines()[-1]
+    if hypotheses and sub_bits >= 1024:
+        # the phase hypotheses find every entry state of the camera frame: the first round only confirms them
+        assert rounds == 1 and "hypotheses: 0 of" in log, log
 
 
 def test_other_samplings_and_sizes(sim, oracle, tmp_path):
@@ -47,8 +50,8 @@ def test_other_samplings_and_sizes(sim, oracle, tmp_path):
     for n in sorted({k.split("/")[0] for k in z.files}):
         jp = str(tmp_path / (n + ".jpg"))
         z[n + "/jpg"].tofile(jp)
-        for sub_bits in (32, 96, 1024):
-            rc, log, out = _run(sim, jp, sub_bits, tmp_path)
+        for sub_bits, hyp in ((32, 0), (96, 1), (1024, 1), (1024, 0)):
+            rc, log, out = _run(sim, jp, sub_bits, tmp_path, hyp)
             if "_rst" in n:
                 assert rc == 3, f"{n}: restart intervals are reported as unsupported ({log})"
                 continue
