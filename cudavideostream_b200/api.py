@@ -193,7 +193,8 @@ class Stream:
         return t.value
 
     def submit_jpeg_raw(self, jpeg_ptr: int, jpeg_bytes: int, diff_ptr: int, show_ptr, text: str, pos_ptr: int, xs_ptr: int) -> int:
-        """cvs_submit_jpeg: the frame arrives as the camera's JPEG bitstream and is decoded on the GPU (nvJPEG)."""
+        """cvs_submit_jpeg: the frame arrives as the camera's JPEG bitstream and is decoded on the GPU (the library's own
+        kernels: OpenCV's pixels bit for bit)."""
         t = C.c_uint64(0)
         _check(load_library().cvs_submit_jpeg(self._h, jpeg_ptr, jpeg_bytes, diff_ptr, show_ptr, text.encode(), pos_ptr, xs_ptr,
                                               C.byref(t)))

@@ -162,6 +162,8 @@ constexpr int kSlots = 4; // tickets that may be outstanding per stream
 
 // scratch of the GPU JPEG decoder (cvs_jpeg.cuh), one set per handle: decodes of a handle are ordered on one stream
 struct JpegDecoder {
+    uint8_t *d_arena = nullptr;   // everything below points into this one allocation
+    size_t zero_bytes_fixed = 0;  // bytes in front of the coefficients that every decode clears
     uint8_t *d_raw = nullptr, *d_unst = nullptr; // entropy-coded segment as received / unstuffed (zero-padded)
     size_t raw_cap = 0;
     uint32_t *d_block_kept = nullptr, *d_total_bits = nullptr;
@@ -181,13 +183,7 @@ struct JpegDecoder {
     size_t block_cap = 0;
     int coop_blocks_per_sm = 0;
     uint32_t sub_bits = 1024;
-    void release()
-    {
-        cudaFree(d_raw); cudaFree(d_unst); cudaFree(d_block_kept); cudaFree(d_total_bits); cudaFree(d_tables);
-        cudaFree(d_entry); cudaFree(d_used); cudaFree(d_nblk); cudaFree(d_tile_blk); cudaFree(d_dcs); cudaFree(d_tile_dc);
-        cudaFree(d_changed); cudaFree(d_coef); cudaFree(d_planes);
-        cudaFree(d_hx); cudaFree(d_hy); cudaFree(d_hmap); cudaFree(d_mid_state); cudaFree(d_mid_nblk); cudaFree(d_mid_dc);
-    }
+    void release() { cudaFree(d_arena); }
 };
 
 struct Slot {
@@ -292,7 +288,8 @@ struct cvs_stream_s {
     cudaEvent_t ev_base = nullptr;
     bool push_payload = true; // CVS_PAYLOAD_PUSH=0 falls back to count round trip + copy engine
     bool speculate = true;    // CVS_EGRESS_SPECULATE=0: cvs_submit_io never copies a predicted payload size
-    bool coop = true;          // CVS_COOP=0: plain launches instead of cooperative ones (measurements only)
+    int coop = -1;             // CVS_COOP: 1 = every stream-kernel launch cooperative, 0 = none; default (-1): sequences
+                               // cooperative, single frames (the submit / exec path) plain -- see run_frames
     int push_blocks = 0;       // CVS_PUSH_BLOCKS: grid of the payload push kernel (0 = one block per SM)
     bool speculate_all = false; // CVS_EGRESS_SPECULATE=2: ... and 2: also for payloads above N/4 entries (measurements)
     uint32_t pred = 0;        // predicted entries of the next frame (previous count + margin)
@@ -622,9 +619,18 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
             p.debug = h->debug;
             p.status = d_status;
             void *args[] = {&p};
-            if (h->coop)
+            // The blocks only ever wait for blocks of LOWER index of the same step (look-back), never at a grid barrier, and
+            // G <= the blocks the device can hold, so a plain launch cannot deadlock (blocks are dispatched in index
+            // order); a cooperative launch additionally waits until the WHOLE grid fits at once.  Sequences keep that
+            // (every block starts together: the timings of DESIGN 4.1); a single frame of the submit / exec path is
+            // launched plain, so that its blocks start as SMs become free instead of draining the device first -- with
+            // several camera streams on a GPU, whose decode kernels (cvs_jpeg.cuh) and payload pushes would otherwise
+            // run strictly one after the other: 3 JPEG streams 3.8 k -> 7.1 k frames/s, raw streams unchanged.
+            // (frames walked in several segments wait for the totals of ALL blocks of the previous segment: cooperative)
+            const bool coop = h->coop < 0 ? (piece > 1 || nseg > 1) : h->coop != 0;
+            if (coop)
                 CU_TRY(cudaLaunchCooperativeKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
-            else // measurement switch (CVS_COOP=0): the co-residency of the G blocks is then the caller's business
+            else
                 CU_TRY(cudaLaunchKernel((const void *)kern, dim3(G), dim3(block_threads), args, (size_t)smem_bytes, st));
             h->launches++;
         }
@@ -749,7 +755,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
         h->speculate_all = atoi(sp) == 2;
     }
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
-    if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0;
+    if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0 ? 1 : 0;
     if (const char *jd = getenv("CVS_JPEG_DECODER")) h->jpeg_decoder = !strcmp(jd, "own") ? 1 : (!strcmp(jd, "nvjpeg") ? 2 : 0);
     if (const char *hy = getenv("CVS_JPEG_HYPOTHESES")) h->jd.hypotheses = atoi(hy) != 0;
     if (const char *sb = getenv("CVS_JPEG_SUB_BITS")) { // subsequence length of the parallel Huffman decode (measurements)
@@ -975,54 +981,60 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     if (g.width != h->width || g.height != h->height)
         return fail(CVS_ERR_INVALID, "JPEG is %dx%d, the stream is %dx%d", g.width, g.height, h->width, h->height);
 
-    // ---- scratch
+    // ---- scratch: one arena, carved; the part every decode needs zeroed (round counters, entry states, the unstuffed
+    //      string's padding, the coefficients) sits in front so that one memset clears it
     const size_t raw_pad = round_up(P.scan_bytes, 4096) + 4096;
-    if (raw_pad > jd.raw_cap) {
-        CU_TRY(cudaStreamSynchronize(st));
-        cudaFree(jd.d_raw); cudaFree(jd.d_unst); cudaFree(jd.d_block_kept);
-        jd.d_raw = jd.d_unst = nullptr; jd.d_block_kept = nullptr; jd.raw_cap = 0;
-        const size_t cap = raw_pad + raw_pad / 2;
-        CU_TRY(cudaMalloc(&jd.d_raw, cap));
-        CU_TRY(cudaMalloc(&jd.d_unst, cap));
-        CU_TRY(cudaMalloc(&jd.d_block_kept, (cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)));
-        jd.raw_cap = cap;
-    }
-    if (!jd.d_total_bits) {
-        CU_TRY(cudaMalloc(&jd.d_total_bits, sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_tables, sizeof(J::Tables)));
-        CU_TRY(cudaMalloc(&jd.d_changed, J::kMaxRounds * sizeof(unsigned int)));
-    }
-    const size_t nsub_cap = (jd.raw_cap * 8 + jd.sub_bits - 1) / jd.sub_bits + 1;
-    if (nsub_cap > jd.sub_cap) {
-        CU_TRY(cudaStreamSynchronize(st));
-        cudaFree(jd.d_entry); cudaFree(jd.d_used); cudaFree(jd.d_nblk); cudaFree(jd.d_tile_blk); cudaFree(jd.d_dcs); cudaFree(jd.d_tile_dc);
-        cudaFree(jd.d_hx); cudaFree(jd.d_hy); cudaFree(jd.d_hmap); cudaFree(jd.d_mid_state); cudaFree(jd.d_mid_nblk); cudaFree(jd.d_mid_dc);
-        jd.d_mid_state = jd.d_mid_nblk = nullptr; jd.d_mid_dc = nullptr;
-        jd.d_entry = jd.d_used = jd.d_nblk = jd.d_tile_blk = jd.d_hx = jd.d_hy = nullptr; jd.d_dcs = jd.d_tile_dc = nullptr;
-        jd.d_hmap = nullptr; jd.sub_cap = 0;
-        const size_t ntile_cap = nsub_cap / J::kEntropyThreads + 2;
-        CU_TRY(cudaMalloc(&jd.d_entry, (nsub_cap + 2) * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_used, nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_nblk, nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_dcs, 3 * nsub_cap * sizeof(int32_t)));
-        CU_TRY(cudaMalloc(&jd.d_tile_blk, ntile_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_tile_dc, 3 * ntile_cap * sizeof(int32_t)));
-        CU_TRY(cudaMalloc(&jd.d_hx, 6 * nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_hy, 6 * nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_hmap, 16 * nsub_cap));
-        CU_TRY(cudaMalloc(&jd.d_mid_state, J::kMaxSplit * nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_mid_nblk, J::kMaxSplit * nsub_cap * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&jd.d_mid_dc, 3 * J::kMaxSplit * nsub_cap * sizeof(int32_t)));
-        jd.sub_cap = nsub_cap;
-    }
     const size_t luma_bytes = (size_t)g.mcux * 8 * g.H * g.mcuy * 8 * g.V, chroma_bytes = (size_t)g.mcux * 8 * g.mcuy * 8;
-    if (g.nblocks > jd.block_cap) {
+    if (raw_pad > jd.raw_cap || g.nblocks > jd.block_cap) {
+        const size_t raw_cap = std::max(jd.raw_cap, raw_pad + raw_pad / 2), block_cap = std::max<size_t>(jd.block_cap, g.nblocks);
         CU_TRY(cudaStreamSynchronize(st));
-        cudaFree(jd.d_coef); cudaFree(jd.d_planes);
-        jd.d_coef = nullptr; jd.d_planes = nullptr; jd.block_cap = 0;
-        CU_TRY(cudaMalloc(&jd.d_coef, (size_t)g.nblocks * 64 * sizeof(int16_t)));
-        CU_TRY(cudaMalloc(&jd.d_planes, (size_t)g.nblocks * 64 + 256));
-        jd.block_cap = g.nblocks;
+        cudaFree(jd.d_arena);
+        jd.d_arena = nullptr;
+        jd.raw_cap = jd.block_cap = jd.sub_cap = 0;
+        const size_t nsub_cap = (raw_cap * 8 + jd.sub_bits - 1) / jd.sub_bits + 1, ntile_cap = nsub_cap / J::kEntropyThreads + 2;
+        size_t off = 0;
+        auto carve = [&](size_t bytes) {
+            const size_t o = off;
+            off += round_up(bytes, 256);
+            return o;
+        };
+        const size_t o_changed = carve(J::kMaxRounds * sizeof(unsigned int)), o_entry = carve((nsub_cap + 2) * sizeof(uint32_t)),
+                     o_unst = carve(raw_cap), o_coef = carve(block_cap * 64 * sizeof(int16_t));
+        jd.zero_bytes_fixed = o_coef; // + nblocks * 128 of the coefficients
+        const size_t o_raw = carve(raw_cap), o_kept = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),
+                     o_total = carve(sizeof(uint32_t)), o_tables = carve(sizeof(J::Tables)), o_used = carve(nsub_cap * sizeof(uint32_t)),
+                     o_nblk = carve(nsub_cap * sizeof(uint32_t)), o_dcs = carve(3 * nsub_cap * sizeof(int32_t)),
+                     o_tile_blk = carve(ntile_cap * sizeof(uint32_t)), o_tile_dc = carve(3 * ntile_cap * sizeof(int32_t)),
+                     o_hx = carve(6 * nsub_cap * sizeof(uint32_t)), o_hy = carve(6 * nsub_cap * sizeof(uint32_t)),
+                     o_hmap = carve(16 * nsub_cap), o_mid_state = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
+                     o_mid_nblk = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
+                     o_mid_dc = carve(3 * J::kMaxSplit * nsub_cap * sizeof(int32_t)), o_planes = carve(block_cap * 64 + 256);
+        CU_TRY(cudaMalloc(&jd.d_arena, off));
+        uint8_t *a = jd.d_arena;
+        jd.d_changed = reinterpret_cast<unsigned int *>(a + o_changed);
+        jd.d_entry = reinterpret_cast<uint32_t *>(a + o_entry);
+        jd.d_unst = a + o_unst;
+        jd.d_coef = reinterpret_cast<int16_t *>(a + o_coef);
+        jd.d_raw = a + o_raw;
+        jd.d_block_kept = reinterpret_cast<uint32_t *>(a + o_kept);
+        jd.d_total_bits = reinterpret_cast<uint32_t *>(a + o_total);
+        jd.d_tables = reinterpret_cast<J::Tables *>(a + o_tables);
+        jd.d_used = reinterpret_cast<uint32_t *>(a + o_used);
+        jd.d_nblk = reinterpret_cast<uint32_t *>(a + o_nblk);
+        jd.d_dcs = reinterpret_cast<int32_t *>(a + o_dcs);
+        jd.d_tile_blk = reinterpret_cast<uint32_t *>(a + o_tile_blk);
+        jd.d_tile_dc = reinterpret_cast<int32_t *>(a + o_tile_dc);
+        jd.d_hx = reinterpret_cast<uint32_t *>(a + o_hx);
+        jd.d_hy = reinterpret_cast<uint32_t *>(a + o_hy);
+        jd.d_hmap = a + o_hmap;
+        jd.d_mid_state = reinterpret_cast<uint32_t *>(a + o_mid_state);
+        jd.d_mid_nblk = reinterpret_cast<uint32_t *>(a + o_mid_nblk);
+        jd.d_mid_dc = reinterpret_cast<int32_t *>(a + o_mid_dc);
+        jd.d_planes = a + o_planes;
+        jd.raw_cap = raw_cap;
+        jd.block_cap = block_cap;
+        jd.sub_cap = nsub_cap;
+        jd.tables_valid = false;
     }
     if (!jd.tables_valid || memcmp(&jd.tables_host, &P.t, sizeof(J::Tables)) != 0) {
         // rare (a camera sends the same tables with every frame); the pageable source is staged before the call returns
@@ -1034,15 +1046,13 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     // ---- the entropy-coded segment crosses PCIe (0.4 MB instead of the 6.2 MB frame), FF 00 -> FF
     const uint32_t raw_len = (uint32_t)P.scan_bytes;
     CU_TRY(cudaMemcpyAsync(jd.d_raw, jpeg + P.scan_offset, raw_len, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(jd.d_unst, 0, round_up(raw_len, 4096) + 64, st));
+    CU_TRY(cudaMemsetAsync(jd.d_arena, 0, jd.zero_bytes_fixed + (size_t)g.nblocks * 64 * sizeof(int16_t), st));
     const uint32_t ublocks = (raw_len + J::kUnstuffThreads * J::kUnstuffBytes - 1) / (J::kUnstuffThreads * J::kUnstuffBytes);
     J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept);
     J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_unst, jd.d_total_bits);
 
     // ---- Huffman decode: one cooperative launch (sync rounds, prefix sums, coefficient write)
-    CU_TRY(cudaMemsetAsync(jd.d_changed, 0, J::kMaxRounds * sizeof(unsigned int), st));
-    CU_TRY(cudaMemsetAsync(jd.d_entry, 0, ((size_t)g.nsub_max + 2) * sizeof(uint32_t), st)); // first guess: a block starts here
-    CU_TRY(cudaMemsetAsync(jd.d_coef, 0, (size_t)g.nblocks * 64 * sizeof(int16_t), st));
+    // (entry states start as zero = "a block of phase 0 starts here": the first guess when the hypotheses are switched off)
     if (!jd.coop_blocks_per_sm) {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jd.coop_blocks_per_sm, J::k_entropy, J::kEntropyThreads, 0));
         if (jd.coop_blocks_per_sm < 1) return fail(CVS_ERR_INTERNAL, "k_entropy does not fit an SM");

@@ -233,13 +233,23 @@ cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int heig
  * Capture-side decode on the GPU.  The reference's camera delivers MJPG and OpenCV
  * decodes it on the CPU before exec_core sees the frame (server/src/threads.cpp:32-41; "read 37 ms",
  * REPORT/report.tex:914).  cvs_submit_jpeg takes the camera's JPEG bitstream instead of the decoded frame: ~0.4 MB
- * cross PCIe instead of 6.2 MB (1080p), nvJPEG (loaded with dlopen on first use) decodes into the slot's upload
- * buffer and the rest of the path is unchanged.  The decoder is NVIDIA's, not libjpeg-turbo: with interpolating
- * chroma upsampling (the default here, as in libjpeg-turbo) the decoded pixels of the reference's own f1.jpg / f2.jpg
- * differ from OpenCV's by at most 5 (mean 0.64) and the K1 count is 370,732 instead of 369,350
- * (tests/test_jpeg_ingest.py), so a payload produced this way equals the reference's only up to the decoder --
- * opt-in, like the wire format.  On the pool's boxes nvJPEG decodes ~200 1080p frames/s per stream (its Huffman stage
- * runs on the host; the hardware JPEG engine is not exposed), so today this entry point saves PCIe bytes, not time.
+ * cross PCIe instead of 6.2 MB (1080p), the library's own kernels (csrc/cvs_jpeg.cuh) decode it into the slot's
+ * upload buffer and the rest of the path is unchanged.
+ *   The decoder reproduces OpenCV's (libjpeg-turbo's default) arithmetic -- sequential-DCT Huffman decoding, the
+ *   accurate integer IDCT (jidctint.c), "fancy" chroma upsampling with replicated border rows (jdsample.c /
+ *   jdmainct.c), fixed-point YCbCr -> RGB (jdcolor.c) -- so the pixels are bit for bit the ones the reference's
+ *   capture thread would have produced: on the reference's own f1.jpg / f2.jpg the payload is the reference's, K1 =
+ *   369,350 (tests/test_jpeg_ingest.py; oracle: oracle/jpeg_oracle.c, pinned against cv2).
+ *   Covered: baseline (SOF0/SOF1 Huffman, 8 bit), one interleaved scan, Y Cb Cr with luma sampling 1x1 / 2x1 / 2x2
+ *   and chroma 1x1 (what UVC cameras and cv2.imwrite produce), or one gray component; no restart intervals.
+ *   Other forms (restart intervals, progressive ...) go to nvJPEG (loaded with dlopen on first use), whose pixels
+ *   are close to but not identical with libjpeg-turbo's (<= 5 apart on the fixture frames); CVS_JPEG_DECODER=own
+ *   refuses them instead, CVS_JPEG_DECODER=nvjpeg sends everything there (measurements).
+ *   A damaged entropy-coded segment never writes outside the frame; when the decoder notices (the stream holds
+ *   fewer blocks than the image, or the parallel decode does not settle) cvs_wait / cvs_sequence_status return
+ *   CVS_ERR_INVALID for that frame.
+ *   1080p camera frame (432 KB): 0.32 ms per decode on one stream, ~10,000 decodes/s with four streams of a GPU
+ *   (nvJPEG on the same box: 205/s) -- profiles/README.md.
  * --------------------------------------------------------------------------------------------------------------- */
 cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *diff_out, uint8_t *show,
                            const char *text, unsigned int *pos, int *xs, uint64_t *ticket);
