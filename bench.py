@@ -586,7 +586,7 @@ def e2e_run(cvs, torch, args, seqs, local, barrier):
     # ---- capture-side decode on the GPU: the camera's JPEG bitstream in, payload out (cvs_submit_jpeg).  Real
     #      camera frames (the reference's own fixture pair, 0.43 MB each instead of 6.2 MB raw), alternating
     try:
-        res["jpeg_ingest"] = jpeg_leg(cvs, torch, local, min(frames_per_density, 200))
+        res["jpeg_ingest"] = jpeg_leg(cvs, torch, local, min(frames_per_density, 200), barrier=barrier)
     except Exception as e:  # nvJPEG missing on the box, fixtures not shipped ...
         res["jpeg_ingest"] = {"unavailable": str(e)[:160]}
 
@@ -620,7 +620,7 @@ def e2e_run(cvs, torch, args, seqs, local, barrier):
     return res
 
 
-def jpeg_leg(cvs, torch, local, nframes, nstreams=3):
+def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
     """frames/s through cvs_submit_jpeg/cvs_wait: H2D of the JPEG bitstream, GPU decode (the library's own kernels,
     cvs_jpeg.cuh: bit for bit OpenCV's pixels), diff+compact, payload D2H -- `nstreams` camera streams interleaved as in
     the e2e leg, one stream alone, and the same camera frames uploaded raw (cvs_submit_io) for comparison."""
@@ -671,20 +671,24 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3):
                 d2h += 4 + 5 * pp[0]
         return h2d, d2h
 
-    def timed(k, ns, jpeg=True):
+    def timed(k, ns, jpeg=True):  # whole job: frames of all ranks / max-over-ranks time
         run(8, ns, jpeg)
         torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         h2d, d2h = run(k, ns, jpeg)
         torch.cuda.synchronize()
-        return k * ns / (time.perf_counter() - t0), h2d, d2h
+        dt = time.perf_counter() - t0
+        dt, (nfr, h2d, d2h) = cvs.sharding.reduce_job(dt, [k * ns, h2d, d2h], torch.device("cuda", local))
+        return nfr / dt, h2d, d2h
 
     v, h2d, d2h = timed(nframes, nstreams)
     v1, _, _ = timed(nframes, 1)
     vr, h2dr, _ = timed(nframes, nstreams, jpeg=False)
     for s in streams:
         s.close()
-    return {"value": v, "unit": "frames/s", "streams": nstreams, "frames": nframes * nstreams, "h2d_bytes": h2d, "d2h_bytes": d2h,
+    return {"value": v, "unit": "frames/s", "streams_per_gpu": nstreams, "frames_per_gpu": nframes * nstreams, "h2d_bytes": h2d,
+            "d2h_bytes": d2h,
             "one_stream": v1, "same_frames_uploaded_raw": {"value": vr, "h2d_bytes": h2dr},
             "decoder": os.environ.get("CVS_JPEG_DECODER", "own (cvs_jpeg.cuh), nvJPEG for forms it does not cover"),
             "note": "the reference's camera frames f1.jpg / f2.jpg alternating (about 6 % of the bytes change) on every stream; "

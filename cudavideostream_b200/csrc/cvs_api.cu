@@ -306,7 +306,10 @@ struct cvs_stream_s {
     unsigned int *h_status = nullptr; // pinned
     unsigned long long *d_desc = nullptr;
     size_t desc_words = 0;
-    JpegDecoder jd;                     // cvs_submit_jpeg / cvs_decode_jpeg_device: the library's own decoder (cvs_jpeg.cuh)
+    JpegDecoder jd[3];                  // the library's own decoder (cvs_jpeg.cuh), scratch allocated on first use: sets 0 / 1
+                                        // for cvs_submit_jpeg on two streams (consecutive frames decode side by side),
+                                        // set 2 for cvs_decode_jpeg_device on the caller's stream
+    cudaStream_t s_jpg[2] = {nullptr, nullptr};
     int jpeg_decoder = 0;               // 0: own decoder, nvJPEG for streams it does not cover; 1: own only; 2: nvJPEG only
     nvjpegHandle_t jpeg = nullptr;      // cvs_submit_jpeg / cvs_decode_jpeg_device: nvJPEG handle (on first use)
     bool jpeg_batched = false;          // the handle's backend wants the batched entry points (hardware engine / GPU Huffman)
@@ -757,10 +760,10 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0 ? 1 : 0;
     if (const char *jd = getenv("CVS_JPEG_DECODER")) h->jpeg_decoder = !strcmp(jd, "own") ? 1 : (!strcmp(jd, "nvjpeg") ? 2 : 0);
-    if (const char *hy = getenv("CVS_JPEG_HYPOTHESES")) h->jd.hypotheses = atoi(hy) != 0;
+    if (const char *hy = getenv("CVS_JPEG_HYPOTHESES")) h->jd[0].hypotheses = h->jd[1].hypotheses = h->jd[2].hypotheses = atoi(hy) != 0;
     if (const char *sb = getenv("CVS_JPEG_SUB_BITS")) { // subsequence length of the parallel Huffman decode (measurements)
         const int v = atoi(sb);
-        if (v >= 64 && v <= 65536 && v % 32 == 0) h->jd.sub_bits = (uint32_t)v;
+        if (v >= 64 && v <= 65536 && v % 32 == 0) h->jd[0].sub_bits = h->jd[1].sub_bits = h->jd[2].sub_bits = (uint32_t)v;
     }
     if (const char *pb = getenv("CVS_PUSH_BLOCKS")) h->push_blocks = atoi(pb);
     memset(&h->weights, 0, sizeof h->weights);
@@ -861,7 +864,9 @@ cvs_status cvs_destroy(cvs_handle h)
     }
     cudaFree(h->d_ref); cudaFree(h->d_lut); cudaFree(h->d_status); cudaFreeHost(h->h_status);
     cudaFree(h->d_band_pos);
-    h->jd.release();
+    for (JpegDecoder &jd : h->jd) jd.release();
+    for (cudaStream_t js : h->s_jpg)
+        if (js) cudaStreamDestroy(js);
     if (h->jpeg_state && g_nvjpeg.ok) g_nvjpeg.StateDestroy(h->jpeg_state);
     if (h->jpeg && g_nvjpeg.ok) g_nvjpeg.Destroy(h->jpeg);
     cudaFree(h->d_desc); cudaFree(h->d_work); cudaFree(h->d_gray1); cudaFree(h->d_hist); cudaFree(h->d_thr);
@@ -964,11 +969,10 @@ static cvs_status jpeg_decode_nvjpeg(cvs_handle h, nvjpegJpegState_t *state, con
 // The library's own decoder (cvs_jpeg.cuh): bit for bit the pixels OpenCV / libjpeg-turbo produce.  `status` receives the
 // decoder's status bits (device word, OR-ed).  *unsupported is set when the bitstream is a JPEG this decoder does not
 // cover (restart intervals, progressive, other samplings); nothing has been enqueued then.
-static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out, cudaStream_t st,
-                                  unsigned int *d_status, bool *unsupported)
+static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
+                                  cudaStream_t st, unsigned int *d_status, bool *unsupported)
 {
     namespace J = cvs::jpg;
-    JpegDecoder &jd = h->jd;
     *unsupported = false;
     static thread_local J::Parsed P;
     const J::ParseStatus ps = J::parse(jpeg, jpeg_bytes, jd.sub_bits, &P);
@@ -1111,12 +1115,12 @@ static cvs_status jpeg_decode_own(cvs_handle h, const uint8_t *jpeg, size_t jpeg
 }
 
 // decode one baseline JPEG of the stream's frame size into d_out (BGR interleaved, pitch 3*width), asynchronously on `st`
-static cvs_status jpeg_decode(cvs_handle h, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
-                              cudaStream_t st, unsigned int *d_status)
+static cvs_status jpeg_decode(cvs_handle h, int set, nvjpegJpegState_t *state, const uint8_t *jpeg, size_t jpeg_bytes,
+                              uint8_t *d_out, cudaStream_t st, unsigned int *d_status)
 {
     if (h->jpeg_decoder != 2) {
         bool unsupported = false;
-        const cvs_status e = jpeg_decode_own(h, jpeg, jpeg_bytes, d_out, st, d_status, &unsupported);
+        const cvs_status e = jpeg_decode_own(h, h->jd[set], jpeg, jpeg_bytes, d_out, st, d_status, &unsupported);
         if (e || !unsupported) return e;
         if (h->jpeg_decoder == 1) return fail(CVS_ERR_INVALID, "JPEG form not covered by the built-in decoder (CVS_JPEG_DECODER=own)");
     }
@@ -1138,17 +1142,25 @@ static cvs_status submit_common(cvs_handle h, const uint8_t *frame, uint8_t *dif
     }
 
     const double th0 = h->trace ? host_us() : 0;
-    // H2D (kernels.cu:461) -- of the raw frame, or of the camera's JPEG bitstream, decoded on the device
-    CU_TRY(cudaEventRecord(s.ev_h2d0, h->s_h2d));
+    // H2D (kernels.cu:461) -- of the raw frame, or of the camera's JPEG bitstream, decoded on the device.  JPEG tickets
+    // alternate between two decode streams with their own scratch: frame t+1 is decoded beside frame t (a decode is a
+    // latency chain that leaves most of the GPU idle); the stream kernel below still takes the frames in ticket order.
+    cudaStream_t s_in = h->s_h2d;
+    const int jset = (int)(h->next_ticket & 1);
+    if (jpeg_bytes) {
+        if (!h->s_jpg[jset]) CU_TRY(cudaStreamCreateWithFlags(&h->s_jpg[jset], cudaStreamNonBlocking));
+        s_in = h->s_jpg[jset];
+    }
+    CU_TRY(cudaEventRecord(s.ev_h2d0, s_in));
     if (jpeg_bytes) {
         // (the ticket's status word is cleared here, in front of the decoder that may raise bits in it)
-        CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), h->s_h2d));
-        st = jpeg_decode(h, &s.jpeg_state, frame, jpeg_bytes, s.d_in, h->s_h2d, s.d_status);
+        CU_TRY(cudaMemsetAsync(s.d_status, 0, sizeof(unsigned int), s_in));
+        st = jpeg_decode(h, jset, &s.jpeg_state, frame, jpeg_bytes, s.d_in, s_in, s.d_status);
         if (st) return st;
     } else {
         CU_TRY(cudaMemcpyAsync(s.d_in, frame, h->N, cudaMemcpyHostToDevice, h->s_h2d));
     }
-    CU_TRY(cudaEventRecord(s.ev_h2d1, h->s_h2d));
+    CU_TRY(cudaEventRecord(s.ev_h2d1, s_in));
     // kernels
     CU_TRY(cudaStreamWaitEvent(h->s_comp, s.ev_h2d1, 0));
     CU_TRY(cudaEventRecord(s.ev_k0, h->s_comp));
@@ -1252,7 +1264,7 @@ cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg
     if (st) return st;
     if (!jpeg || jpeg_bytes == 0 || !d_out) return fail(CVS_ERR_INVALID, "null argument");
     // (status bits of the decoder go to the handle's own status word: cvs_decode_status reads it)
-    st = jpeg_decode(h, &h->jpeg_state, jpeg, jpeg_bytes, d_out, (cudaStream_t)cuda_stream, h->d_status);
+    st = jpeg_decode(h, 2, &h->jpeg_state, jpeg, jpeg_bytes, d_out, (cudaStream_t)cuda_stream, h->d_status);
     if (st) return st;
     CU_TRY(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(unsigned int), cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream));
     return CVS_OK;
