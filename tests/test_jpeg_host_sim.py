@@ -59,3 +59,15 @@ def test_other_samplings_and_sizes(sim, oracle, tmp_path):
             ref = oracle.jpeg_coefficients(z[n + "/jpg"].tobytes())
             got = np.fromfile(out, dtype=np.int16).reshape(-1, 64)
             assert np.array_equal(got, ref), f"{n} S={sub_bits}"
+
+
+def test_frame_without_huffman_tables(sim, oracle, tmp_path):
+    from util import strip_dht
+    with open(os.path.join(GOLDEN, "k1_f2.jpg"), "rb") as f:
+        bare = strip_dht(f.read())
+    jp = str(tmp_path / "bare.jpg")
+    with open(jp, "wb") as f:
+        f.write(bare)
+    rc, log, out = _run(sim, jp, 1024, tmp_path)
+    assert rc == 0, log
+    assert np.array_equal(np.fromfile(out, dtype=np.int16).reshape(-1, 64), oracle.jpeg_coefficients(bare))

@@ -55,6 +55,16 @@ def test_decoded_pixels_of_the_reference_camera_frames_are_opencvs(cvs, oracle, 
     assert oracle.count_difference(frames[0], frames[1], 20) == k1["changed_bytes"] == 369350
 
 
+def test_camera_frames_without_huffman_tables(cvs, oracle, monkeypatch):
+    """MJPG as cameras send it: no DHT segment, the standard tables are implied (OpenCV decodes it; so does the library)."""
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    from util import strip_dht as _strip_dht
+    with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
+        k1 = json.load(f)
+    g = _decode(cvs, _strip_dht(_jpeg("k1_f1.jpg")), 1920, 1080)
+    assert hashlib.sha256(g.tobytes()).hexdigest() == k1["sha256_f1"]
+
+
 @pytest.mark.parametrize("sub_bits", [128, 1024, 4096])
 def test_other_samplings_qualities_and_sizes(cvs, oracle, monkeypatch, sub_bits):
     monkeypatch.setenv("CVS_JPEG_DECODER", "own")

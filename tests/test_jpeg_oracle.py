@@ -9,6 +9,8 @@ import os
 import numpy as np
 import pytest
 
+from util import strip_dht as _strip_dht
+
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -57,3 +59,17 @@ def test_oracle_rejects_what_it_does_not_cover(oracle):
     j[j.index(b"\xff\xc0") + 1] = 0xC2  # progressive SOF
     with pytest.raises(ValueError):
         oracle.jpeg_decode_bgr(bytes(j))
+
+
+def test_frames_without_dht_use_the_standard_tables(oracle):
+    """A camera's MJPG frame may carry no Huffman tables (the standard ones are implied); OpenCV decodes such frames, and
+    so must the oracle -- to the same pixels as the frame that spells the standard tables out."""
+    with open(os.path.join(GOLDEN, "k1_f2.jpg"), "rb") as f:
+        j = f.read()
+    bare = _strip_dht(j)
+    assert len(bare) < len(j) and b"\xff\xc4" not in bare[:600]
+    with open(os.path.join(GOLDEN, "k1_f1_f2.json")) as f:
+        k1 = json.load(f)
+    assert hashlib.sha256(oracle.jpeg_decode_bgr(bare).tobytes()).hexdigest() == k1["sha256_f2"]
+    cv2 = pytest.importorskip("cv2")
+    assert np.array_equal(cv2.imdecode(np.frombuffer(bare, np.uint8), cv2.IMREAD_COLOR), oracle.jpeg_decode_bgr(bare))

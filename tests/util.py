@@ -40,3 +40,17 @@ def run_oracle_sequence(oracle, width, height, base, frames, **kw):
     ref = core.reference()
     core.close()
     return out, ref
+
+
+def strip_dht(jpg: bytes) -> bytes:
+    """The JPEG without its DHT segments (MJPG as cameras send it: the standard Huffman tables are implied)."""
+    out, i = bytearray(jpg[:2]), 2
+    while i < len(jpg):
+        m, ln = jpg[i + 1], (jpg[i + 2] << 8) | jpg[i + 3]
+        if m == 0xDA:
+            out += jpg[i:]
+            break
+        if m != 0xC4:
+            out += jpg[i:i + 2 + ln]
+        i += 2 + ln
+    return bytes(out)
