@@ -166,7 +166,8 @@ struct JpegDecoder {
     size_t zero_bytes_fixed = 0;  // bytes in front of the coefficients that every decode clears
     uint8_t *d_raw = nullptr, *d_unst = nullptr; // entropy-coded segment as received / unstuffed (zero-padded)
     size_t raw_cap = 0;
-    uint32_t *d_block_kept = nullptr, *d_total_bits = nullptr;
+    uint32_t *d_block_kept = nullptr, *d_block_marks = nullptr, *d_total_bits = nullptr, *d_total_marks = nullptr, *d_seg_start = nullptr;
+    uint32_t seg_cap = 0;
     cvs::jpg::Tables *d_tables = nullptr;
     cvs::jpg::Tables tables_host;  // what d_tables holds
     bool tables_valid = false;
@@ -1006,7 +1007,8 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
                      o_unst = carve(raw_cap), o_coef = carve(block_cap * 64 * sizeof(int16_t));
         jd.zero_bytes_fixed = o_coef; // + nblocks * 128 of the coefficients
         const size_t o_raw = carve(raw_cap), o_kept = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),
-                     o_total = carve(sizeof(uint32_t)), o_tables = carve(sizeof(J::Tables)), o_used = carve(nsub_cap * sizeof(uint32_t)),
+                     o_marks = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),
+                     o_seg = carve((block_cap + 2) * sizeof(uint32_t)), o_total = carve(2 * sizeof(uint32_t)), o_tables = carve(sizeof(J::Tables)), o_used = carve(nsub_cap * sizeof(uint32_t)),
                      o_nblk = carve(nsub_cap * sizeof(uint32_t)), o_dcs = carve(3 * nsub_cap * sizeof(int32_t)),
                      o_tile_blk = carve(ntile_cap * sizeof(uint32_t)), o_tile_dc = carve(3 * ntile_cap * sizeof(int32_t)),
                      o_hx = carve(6 * nsub_cap * sizeof(uint32_t)), o_hy = carve(6 * nsub_cap * sizeof(uint32_t)),
@@ -1021,7 +1023,11 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
         jd.d_coef = reinterpret_cast<int16_t *>(a + o_coef);
         jd.d_raw = a + o_raw;
         jd.d_block_kept = reinterpret_cast<uint32_t *>(a + o_kept);
+        jd.d_block_marks = reinterpret_cast<uint32_t *>(a + o_marks);
+        jd.d_seg_start = reinterpret_cast<uint32_t *>(a + o_seg);
+        jd.seg_cap = (uint32_t)block_cap + 2;
         jd.d_total_bits = reinterpret_cast<uint32_t *>(a + o_total);
+        jd.d_total_marks = jd.d_total_bits + 1;
         jd.d_tables = reinterpret_cast<J::Tables *>(a + o_tables);
         jd.d_used = reinterpret_cast<uint32_t *>(a + o_used);
         jd.d_nblk = reinterpret_cast<uint32_t *>(a + o_nblk);
@@ -1052,9 +1058,27 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
     CU_TRY(cudaMemcpyAsync(jd.d_raw, jpeg + P.scan_offset, raw_len, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(jd.d_arena, 0, jd.zero_bytes_fixed + (size_t)g.nblocks * 64 * sizeof(int16_t), st));
     const uint32_t ublocks = (raw_len + J::kUnstuffThreads * J::kUnstuffBytes - 1) / (J::kUnstuffThreads * J::kUnstuffBytes);
-    J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept);
-    J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_unst, jd.d_total_bits);
+    J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks);
+    J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks, jd.d_unst,
+                                                                 jd.d_total_bits, jd.d_seg_start, jd.seg_cap, jd.d_total_marks);
 
+    if (P.restart_interval) {
+        // ---- Huffman decode of a scan with restart intervals: one thread per interval (k_entropy_restart)
+        J::RestartParams rp;
+        rp.tables = jd.d_tables;
+        rp.g = g;
+        rp.words = reinterpret_cast<const uint32_t *>(jd.d_unst);
+        rp.total_bits = jd.d_total_bits;
+        rp.total_marks = jd.d_total_marks;
+        rp.seg_start = jd.d_seg_start;
+        const uint32_t mcus = (uint32_t)g.mcux * (uint32_t)g.mcuy;
+        rp.nseg = (mcus + P.restart_interval - 1) / P.restart_interval;
+        rp.blocks_per_seg = P.restart_interval * (uint32_t)g.bpm;
+        rp.coef = jd.d_coef;
+        rp.status = d_status;
+        if (rp.nseg + 1 > jd.seg_cap) return fail(CVS_ERR_INTERNAL, "restart interval table too small");
+        J::k_entropy_restart<<<(rp.nseg + 127) / 128, 128, 0, st>>>(rp);
+    } else {
     // ---- Huffman decode: one cooperative launch (sync rounds, prefix sums, coefficient write)
     // (entry states start as zero = "a block of phase 0 starts here": the first guess when the hypotheses are switched off)
     if (!jd.coop_blocks_per_sm) {
@@ -1092,6 +1116,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
     const uint32_t egrid = std::max(1u, std::min(ntiles, (uint32_t)(jd.coop_blocks_per_sm * h->sms)));
     void *eargs[] = {&ep};
     CU_TRY(cudaLaunchCooperativeKernel((const void *)J::k_entropy, dim3(egrid), dim3(J::kEntropyThreads), eargs, 0, st));
+    }
 
     // ---- IDCT -> planes -> upsampling + colour conversion -> BGR24
     J::PlaneParams pp;

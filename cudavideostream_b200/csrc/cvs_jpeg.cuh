@@ -222,14 +222,12 @@ struct MidRecords {
 // of different blocks, divergent paths would put their latencies in series, and the chain p -> window -> table -> p is
 // what the whole decode waits for.
 template <bool WRITE, bool RECORD = false>
-CVS_HD RunResult run_subsequence(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t i,
-                                 uint32_t entry, const uint8_t *natural, int16_t *coef, uint32_t first_block, int32_t pred0,
-                                 int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
+CVS_HD RunResult run_range(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t begin,
+                           uint32_t end_nominal, uint32_t i, uint32_t entry, const uint8_t *natural, int16_t *coef,
+                           uint32_t first_block, int32_t pred0, int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
 {
     RunResult r;
     int32_t dc0 = pred0, dc1 = pred1, dc2 = pred2;
-    const uint32_t S = g.sub_bits;
-    const uint32_t begin = i * S, end_nominal = begin + S;
     const uint32_t end = end_nominal < total_bits ? end_nominal : total_bits;
     uint32_t p = begin + (entry & 31u), ph = (entry >> 5) & 7u, k = (entry >> 8) & 63u;
     uint32_t blk = first_block, nblocks = 0;
@@ -292,6 +290,15 @@ CVS_HD RunResult run_subsequence(const TableRef &tb, const Geometry &g, const ui
     return r;
 }
 
+template <bool WRITE, bool RECORD = false>
+CVS_HD RunResult run_subsequence(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t i,
+                                 uint32_t entry, const uint8_t *natural, int16_t *coef, uint32_t first_block, int32_t pred0,
+                                 int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
+{
+    return run_range<WRITE, RECORD>(tb, g, words, total_bits, i * g.sub_bits, i * g.sub_bits + g.sub_bits, i, entry, natural, coef,
+                                    first_block, pred0, pred1, pred2, mid);
+}
+
 } // namespace jpg
 } // namespace cvs
 
@@ -314,10 +321,13 @@ constexpr int kEntropyThreads = 256;
 constexpr unsigned int kJpegNotConverged = 1u << 8, kJpegBlockCount = 1u << 9;
 
 // ---- byte unstuffing ------------------------------------------------------------------------------------------------
-// a byte is dropped when it is the 00 behind an FF (T.81 B.1.1.5); raw_len is the length of the entropy-coded segment
-__device__ __forceinline__ uint32_t unstuff_keep_mask(const uint8_t *raw, uint32_t raw_len, uint32_t first, uint8_t (&b)[kUnstuffBytes])
+// A byte is dropped when it is the 00 behind an FF (T.81 B.1.1.5) or part of a restart marker FF D0..D7; what remains is
+// the plain bit string of the scan, restart intervals back to back (each ends padded to a byte).  raw_len is the length
+// of the entropy-coded segment.  *marks: bit j set = byte j is the second byte of a restart marker.
+__device__ __forceinline__ uint32_t unstuff_keep_mask(const uint8_t *raw, uint32_t raw_len, uint32_t first, uint8_t (&b)[kUnstuffBytes],
+                                                      uint32_t *marks)
 {
-    uint32_t keep = 0;
+    uint32_t keep = 0, mk = 0;
     uint8_t prev = first ? raw[first - 1] : 0;
     if (first + kUnstuffBytes <= raw_len) {
         const uint4 v = *reinterpret_cast<const uint4 *>(raw + first);
@@ -328,67 +338,96 @@ __device__ __forceinline__ uint32_t unstuff_keep_mask(const uint8_t *raw, uint32
 #pragma unroll
         for (int j = 0; j < kUnstuffBytes; j++) b[j] = first + j < raw_len ? raw[first + j] : 0;
     }
+    const uint8_t after = first + kUnstuffBytes < raw_len ? raw[first + kUnstuffBytes] : 0;
 #pragma unroll
     for (int j = 0; j < kUnstuffBytes; j++) {
-        if (first + j < raw_len && !(b[j] == 0x00 && prev == 0xFF)) keep |= 1u << j;
+        const uint8_t next = j + 1 < kUnstuffBytes ? b[j + 1 < kUnstuffBytes ? j + 1 : j] : after;
+        const bool stuffed = b[j] == 0x00 && prev == 0xFF;
+        const bool marker2 = (b[j] & 0xF8) == 0xD0 && prev == 0xFF;
+        const bool marker1 = b[j] == 0xFF && (next & 0xF8) == 0xD0;
+        if (first + j < raw_len) {
+            if (!(stuffed || marker1 || marker2)) keep |= 1u << j;
+            if (marker2) mk |= 1u << j;
+        }
         prev = b[j];
     }
+    *marks = mk;
     return keep;
 }
 
-__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_count(const uint8_t *__restrict__ raw, uint32_t raw_len, uint32_t *block_kept)
+__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_count(const uint8_t *__restrict__ raw, uint32_t raw_len, uint32_t *block_kept,
+                                                                  uint32_t *block_marks)
 {
-    __shared__ uint32_t wsum[kUnstuffThreads / 32];
+    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
     const uint32_t first = (blockIdx.x * kUnstuffThreads + threadIdx.x) * kUnstuffBytes;
     uint8_t b[kUnstuffBytes];
-    uint32_t n = first < raw_len ? (uint32_t)__popc(unstuff_keep_mask(raw, raw_len, first, b)) : 0u;
+    uint32_t mk = 0;
+    uint32_t n = first < raw_len ? (uint32_t)__popc(unstuff_keep_mask(raw, raw_len, first, b, &mk)) : 0u;
     n = __reduce_add_sync(0xffffffffu, n);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = n;
+    const uint32_t m = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mk));
+    if ((threadIdx.x & 31) == 0) {
+        wsum[0][threadIdx.x >> 5] = n;
+        wsum[1][threadIdx.x >> 5] = m;
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 2) {
         uint32_t t = 0;
-        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[w];
-        block_kept[blockIdx.x] = t;
+        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[threadIdx.x][w];
+        (threadIdx.x ? block_marks : block_kept)[blockIdx.x] = t;
     }
 }
 
-// out must be zero beyond the string (the decoder looks up to 8 bytes past its end); total_bits <- 8 * kept bytes
+// out must be zero beyond the string (the decoder looks up to 16 bytes past its end); total_bits <- 8 * kept bytes;
+// seg_start[m] <- byte offset (in out) at which restart interval m starts (seg_start[0] = 0 is the caller's),
+// total_marks <- number of restart markers
 __global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t *__restrict__ raw, uint32_t raw_len,
-                                                                  const uint32_t *__restrict__ block_kept, uint8_t *out,
-                                                                  uint32_t *total_bits)
+                                                                  const uint32_t *__restrict__ block_kept,
+                                                                  const uint32_t *__restrict__ block_marks, uint8_t *out,
+                                                                  uint32_t *total_bits, uint32_t *seg_start, uint32_t seg_cap,
+                                                                  uint32_t *total_marks)
 {
-    __shared__ uint32_t wsum[kUnstuffThreads / 32];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
+    __shared__ uint32_t s_base[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // bytes kept by the blocks in front of this one
-    uint32_t part = 0;
-    for (uint32_t j = tid; j < blockIdx.x; j += kUnstuffThreads) part += block_kept[j];
+    // bytes kept / markers seen by the blocks in front of this one
+    uint32_t part = 0, partm = 0;
+    for (uint32_t j = tid; j < blockIdx.x; j += kUnstuffThreads) {
+        part += block_kept[j];
+        partm += block_marks[j];
+    }
     part = __reduce_add_sync(0xffffffffu, part);
-    if (lane == 0) wsum[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[w];
-        s_base = t;
+    partm = __reduce_add_sync(0xffffffffu, partm);
+    if (lane == 0) {
+        wsum[0][warp] = part;
+        wsum[1][warp] = partm;
     }
     __syncthreads();
-    const uint32_t base = s_base;
+    if (tid < 2) {
+        uint32_t t = 0;
+        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[tid][w];
+        s_base[tid] = t;
+    }
+    __syncthreads();
+    const uint32_t base = s_base[0], basem = s_base[1];
     __syncthreads();
     const uint32_t first = (blockIdx.x * kUnstuffThreads + tid) * kUnstuffBytes;
     uint8_t b[kUnstuffBytes];
-    const uint32_t keep = first < raw_len ? unstuff_keep_mask(raw, raw_len, first, b) : 0u;
-    const uint32_t n = (uint32_t)__popc(keep);
-    uint32_t incl = n;
+    uint32_t mk = 0;
+    const uint32_t keep = first < raw_len ? unstuff_keep_mask(raw, raw_len, first, b, &mk) : 0u;
+    const uint32_t n = (uint32_t)__popc(keep), nm = (uint32_t)__popc(mk);
+    uint32_t incl = n | (nm << 16); // both counts in one scan (a block keeps <= 4096 bytes and sees <= 2048 markers)
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= (uint32_t)d) incl += o;
     }
-    if (lane == 31) wsum[warp] = incl;
+    if (lane == 31) wsum[0][warp] = incl;
     __syncthreads();
     uint32_t woff = 0;
-    for (uint32_t w = 0; w < warp; w++) woff += wsum[w];
-    uint32_t o = base + woff + incl - n;
+    for (uint32_t w = 0; w < warp; w++) woff += wsum[0][w];
+    const uint32_t excl = woff + incl - (n | (nm << 16));
+    uint32_t o = base + (excl & 0xffffu);
+    uint32_t mi = basem + (excl >> 16);
     if (keep == 0xffffu && (o & 3u) == 0) { // the common case: nothing dropped, word-aligned destination
         uint32_t *dst = reinterpret_cast<uint32_t *>(out + o);
 #pragma unroll
@@ -396,14 +435,64 @@ __global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t
             dst[q] = (uint32_t)b[4 * q] | ((uint32_t)b[4 * q + 1] << 8) | ((uint32_t)b[4 * q + 2] << 16) | ((uint32_t)b[4 * q + 3] << 24);
     } else {
 #pragma unroll
-        for (int j = 0; j < kUnstuffBytes; j++)
+        for (int j = 0; j < kUnstuffBytes; j++) {
             if (keep >> j & 1u) out[o++] = b[j];
+            if (mk >> j & 1u) { // the next restart interval starts at the byte that follows
+                ++mi;
+                if (mi < seg_cap) seg_start[mi] = o;
+            }
+        }
     }
     if (blockIdx.x == gridDim.x - 1 && tid == kUnstuffThreads - 1) {
         uint32_t t = 0;
-        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[w];
-        *total_bits = 8u * (base + t);
+        for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[0][w];
+        *total_bits = 8u * (base + (t & 0xffffu));
+        *total_marks = basem + (t >> 16);
     }
+}
+
+// ---- entropy decode, scans with restart intervals: every interval starts byte-aligned in a known state (first block of
+//      its MCUs, predictors zero), so one thread decodes one interval straight into the coefficients -- no
+//      synchronisation, no counting pass.  (Parallel only across intervals: a camera that puts a whole MCU row into one
+//      interval gets 68 sequential chains per 1080p frame, about 1 ms; intervals of a few MCUs decode in microseconds.)
+struct RestartParams {
+    const Tables *tables;
+    Geometry g;
+    const uint32_t *words;
+    const uint32_t *total_bits, *total_marks;
+    const uint32_t *seg_start; // [nseg]
+    uint32_t nseg;             // ceil(MCUs / restart interval)
+    uint32_t blocks_per_seg;   // restart interval * blocks per MCU
+    int16_t *coef;
+    unsigned int *status;
+};
+
+__global__ void __launch_bounds__(128) k_entropy_restart(const RestartParams p)
+{
+    __shared__ Tables tb;
+    __shared__ uint8_t s_nat[64];
+    const uint32_t tid = threadIdx.x;
+    if (tid < 64) s_nat[tid] = c_natural[tid];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(p.tables);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&tb);
+        for (uint32_t j = tid; j < sizeof(Tables) / 4; j += blockDim.x) dst[j] = src[j];
+    }
+    __syncthreads();
+    const TableRef tbr = table_ref(&tb);
+    const uint32_t T = *p.total_bits;
+    if (blockIdx.x == 0 && tid == 0 && *p.total_marks + 1 != p.nseg) atomicOr(p.status, kJpegBlockCount);
+    const uint32_t sgm = blockIdx.x * blockDim.x + tid;
+    if (sgm >= p.nseg) return;
+    const uint32_t begin = sgm ? 8u * p.seg_start[sgm] : 0u;
+    uint32_t end = sgm + 1 < p.nseg ? 8u * p.seg_start[sgm + 1] : T;
+    if (begin >= T || end > T || end <= begin) return; // fewer markers than intervals: reported above
+    Geometry g = p.g;
+    const uint32_t first = sgm * p.blocks_per_seg;
+    // the interval's blocks only: a damaged interval must not spill into its neighbour's coefficients
+    g.nblocks = min(p.g.nblocks, first + p.blocks_per_seg);
+    const RunResult r = run_range<true>(tbr, g, p.words, end, begin, end, 0, pack_state(0, 0, 0), s_nat, p.coef, first, 0, 0, 0);
+    if (first + r.nblocks < g.nblocks) atomicOr(p.status, kJpegBlockCount);
 }
 
 // ---- entropy decode -------------------------------------------------------------------------------------------------

@@ -15,12 +15,13 @@ struct Parsed {
     Tables t;
     size_t scan_offset = 0; // first byte of the entropy-coded segment
     size_t scan_bytes = 0;  // up to (not including) the EOI marker
+    uint32_t restart_interval = 0; // MCUs per restart interval (DRI); 0: none
 };
 
 enum ParseStatus {
     kParseOk = 0,
     kParseNotJpeg = 1,     // not a JPEG / truncated / inconsistent
-    kParseUnsupported = 2, // a JPEG, but not the form this decoder covers (progressive, restart intervals, other samplings ...)
+    kParseUnsupported = 2, // a JPEG, but not the form this decoder covers (progressive, arithmetic coding, other samplings ...)
 };
 
 static const uint8_t kZigzagNatural[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
@@ -110,6 +111,7 @@ inline bool build_huff(const uint8_t *bits, const uint8_t *vals, int nvals, uint
 inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *out)
 {
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) return kParseNotJpeg;
+    out->restart_interval = 0;
     struct RawHuff {
         uint8_t bits[17];
         uint8_t vals[256];
@@ -197,7 +199,7 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
             return kParseUnsupported; // progressive, lossless, arithmetic coding
         } else if (m == 0xDD) {
             if (pl < 2) return kParseNotJpeg;
-            if ((p[0] << 8) | p[1]) return kParseUnsupported; // restart intervals: independent segments, another decoder's job
+            out->restart_interval = (uint32_t)((p[0] << 8) | p[1]);
         } else if (m == 0xDA) {
             if (!sof || pl < 1 || p[0] != ncomp || pl < 1 + 2 * (size_t)ncomp + 3) return sof ? kParseUnsupported : kParseNotJpeg;
             for (int c = 0; c < ncomp; c++) {

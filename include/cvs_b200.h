@@ -241,8 +241,9 @@ cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int heig
  *   capture thread would have produced: on the reference's own f1.jpg / f2.jpg the payload is the reference's, K1 =
  *   369,350 (tests/test_jpeg_ingest.py; oracle: oracle/jpeg_oracle.c, pinned against cv2).
  *   Covered: baseline (SOF0/SOF1 Huffman, 8 bit), one interleaved scan, Y Cb Cr with luma sampling 1x1 / 2x1 / 2x2
- *   and chroma 1x1 (what UVC cameras and cv2.imwrite produce), or one gray component; no restart intervals.
- *   Other forms (restart intervals, progressive ...) go to nvJPEG (loaded with dlopen on first use), whose pixels
+ *   and chroma 1x1 (what UVC cameras and cv2.imwrite produce), or one gray component; with or without restart
+ *   intervals (one thread per interval then); frames without a DHT segment use the standard tables (MJPG).
+ *   Other forms (progressive, arithmetic coding, other samplings) go to nvJPEG (loaded with dlopen on first use), whose pixels
  *   are close to but not identical with libjpeg-turbo's (<= 5 apart on the fixture frames); CVS_JPEG_DECODER=own
  *   refuses them instead, CVS_JPEG_DECODER=nvjpeg sends everything there (measurements).
  *   A damaged entropy-coded segment never writes outside the frame; when the decoder notices (the stream holds

@@ -29,6 +29,10 @@ int main(int argc, char **argv)
         printf("parse status %d\n", (int)ps);
         return ps == kParseUnsupported ? 3 : 4;
     }
+    if (P.restart_interval) { // independent intervals: k_entropy_restart, no synchronisation to simulate
+        printf("restart interval %u\n", P.restart_interval);
+        return 3;
+    }
     // unstuff (k_unstuff_*)
     std::vector<uint8_t> u;
     const uint8_t *raw = d.data() + P.scan_offset;

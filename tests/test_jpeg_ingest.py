@@ -75,30 +75,49 @@ def test_other_samplings_qualities_and_sizes(cvs, oracle, monkeypatch, sub_bits)
     for n in names:
         w, h = (int(v) for v in z[n + "/wh"])
         jpg = z[n + "/jpg"].tobytes()
-        if "_rst" in n:  # restart intervals: not this decoder's form
-            with pytest.raises(cvs.CVSError):
-                _decode(cvs, jpg, w, h)
-            continue
         g = _decode(cvs, jpg, w, h)
         assert hashlib.sha256(g.tobytes()).digest() == z[n + "/sha"].tobytes(), n
         done += 1
-    assert done >= 11
+    assert done >= 13  # includes the two streams with restart intervals (k_entropy_restart)
 
 
-def test_restart_interval_streams_fall_back_to_nvjpeg(cvs, monkeypatch):
+def test_restart_intervals_at_camera_size(cvs, oracle, monkeypatch):
+    """The reference's camera frame re-encoded with restart intervals of 1 MCU, 7 MCUs and one MCU row: every interval is
+    decoded by its own thread; the pixels are still OpenCV's."""
+    cv2 = pytest.importorskip("cv2")
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    src = cv2.imdecode(np.frombuffer(_jpeg("k1_f1.jpg"), np.uint8), cv2.IMREAD_COLOR)
+    for interval, extra in ((1, []), (7, [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422]), (120, [])):
+        ok, enc = cv2.imencode(".jpg", src, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, interval] + extra)
+        assert ok and b"\xff\xdd" in enc.tobytes()[:700]
+        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR).reshape(-1)
+        assert np.array_equal(oracle.jpeg_decode_bgr(enc.tobytes()).reshape(-1), ref)
+        g = _decode(cvs, enc.tobytes(), 1920, 1080)
+        bad = np.flatnonzero(g != ref)
+        assert bad.size == 0, f"interval {interval}: {bad.size} bytes differ, first at {bad[:5]}"
+
+
+def test_other_forms_fall_back_to_nvjpeg(cvs, monkeypatch):
+    """Progressive JPEG is not the built-in decoder's form: nvJPEG takes it (another decoder: the same picture, not the
+    same bits); CVS_JPEG_DECODER=own refuses instead."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    img = np.clip(np.add.outer(np.arange(144) * 1.2, np.arange(256) * 0.7)[:, :, None] + rng.integers(0, 30, (144, 256, 3)), 0, 255)
+    ok, enc = cv2.imencode(".jpg", img.astype(np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    assert ok
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    with pytest.raises(cvs.CVSError) as e:
+        _decode(cvs, enc.tobytes(), 256, 144)
+    assert e.value.status == 1
     monkeypatch.delenv("CVS_JPEG_DECODER", raising=False)
-    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
-    n = "q95_420_rst4_256x144"
-    w, h = (int(v) for v in z[n + "/wh"])
     try:
-        g = _decode(cvs, z[n + "/jpg"].tobytes(), w, h)
-    except cvs.CVSError as e:
-        if e.status == 6:
-            pytest.skip(f"nvJPEG is not available on this box: {e}")
+        g = _decode(cvs, enc.tobytes(), 256, 144)
+    except cvs.CVSError as e2:
+        if e2.status == 6:
+            pytest.skip(f"nvJPEG is not available on this box: {e2}")
         raise
-    import cv2
-    ref = cv2.imdecode(z[n + "/jpg"], cv2.IMREAD_COLOR).reshape(-1)
-    assert np.abs(g.astype(np.int16) - ref.astype(np.int16)).mean() < 2.0  # another decoder: the same picture, not the same bits
+    ref = cv2.imdecode(enc, cv2.IMREAD_COLOR).reshape(-1)
+    assert np.abs(g.astype(np.int16) - ref.astype(np.int16)).mean() < 2.0
 
 
 def test_submit_jpeg_payload_is_the_oracles(cvs, oracle, monkeypatch):
