@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nvjpeg.h>
+#include <vector>
 #include <cooperative_groups.h>
 
 #include <atomic>
@@ -169,6 +170,8 @@ struct JpegDecoder {
     uint32_t *d_block_kept = nullptr, *d_block_marks = nullptr, *d_total_bits = nullptr, *d_total_marks = nullptr, *d_seg_start = nullptr;
     uint32_t seg_cap = 0;
     cvs::jpg::Tables *d_tables = nullptr;
+    cvs::jpg::Parsed parsed;       // header of the last frame ...
+    std::vector<uint8_t> header;   // ... and its bytes up to the scan (a camera repeats them: no table rebuild per frame)
     cvs::jpg::Tables tables_host;  // what d_tables holds
     bool tables_valid = false;
     uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr;
@@ -975,13 +978,17 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
 {
     namespace J = cvs::jpg;
     *unsupported = false;
-    static thread_local J::Parsed P;
-    const J::ParseStatus ps = J::parse(jpeg, jpeg_bytes, jd.sub_bits, &P);
-    if (ps == J::kParseUnsupported) {
-        *unsupported = true;
-        return CVS_OK;
+    J::Parsed &P = jd.parsed;
+    if (!J::reparse_same_header(jpeg, jpeg_bytes, jd.header.data(), jd.header.size(), jd.sub_bits, &P)) {
+        jd.header.clear();
+        const J::ParseStatus ps = J::parse(jpeg, jpeg_bytes, jd.sub_bits, &P);
+        if (ps == J::kParseUnsupported) {
+            *unsupported = true;
+            return CVS_OK;
+        }
+        if (ps != J::kParseOk) return fail(CVS_ERR_INVALID, "not a decodable baseline JPEG");
+        jd.header.assign(jpeg, jpeg + P.scan_offset); // the next frame of the camera starts with the same bytes
     }
-    if (ps != J::kParseOk) return fail(CVS_ERR_INVALID, "not a decodable baseline JPEG");
     const J::Geometry &g = P.g;
     if (g.width != h->width || g.height != h->height)
         return fail(CVS_ERR_INVALID, "JPEG is %dx%d, the stream is %dx%d", g.width, g.height, h->width, h->height);

@@ -249,5 +249,21 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
     return kParseOk;
 }
 
+// A camera repeats the same header (tables, geometry) in front of every frame: when the bytes up to the scan are those of
+// the frame `prev` was parsed from, only the length of the entropy-coded segment has to be found again.
+inline bool reparse_same_header(const uint8_t *d, size_t n, const uint8_t *prev_header, size_t prev_header_bytes, uint32_t sub_bits,
+                                Parsed *prev)
+{
+    if (!prev_header_bytes || n < prev_header_bytes + 2 || prev->g.sub_bits != sub_bits || memcmp(d, prev_header, prev_header_bytes) != 0)
+        return false;
+    size_t end = n;
+    while (end >= prev->scan_offset + 2 && !(d[end - 2] == 0xFF && d[end - 1] == 0xD9)) end--;
+    if (end < prev->scan_offset + 2) return false;
+    prev->scan_bytes = end - 2 - prev->scan_offset;
+    if (prev->scan_bytes == 0 || prev->scan_bytes > 0x1fffffffu) return false;
+    prev->g.nsub_max = (uint32_t)((prev->scan_bytes * 8 + sub_bits - 1) / sub_bits);
+    return true;
+}
+
 } // namespace jpg
 } // namespace cvs
