@@ -153,6 +153,11 @@ CVS_HD TableRef table_ref(const Tables *t) // device: t lives in shared memory
 // word (p >> 5) + 3 and nobody reads its result before a later call, so a warp (which issues in order and waits at the
 // first instruction that reads a loaded register) never waits for memory on the token chain.
 // p may advance by at most 31 bits between two calls (a token is at most 16 + 15 bits long).
+// (Measured and not adopted: the window as a 64-bit shift register that is shifted by the token length and refilled by
+//  OR -- no selects between table entry and next window -- together with an 11-bit first-level table: X / Y / W phases
+//  136 us instead of 123 us, 335 us instead of 317 us per frame.  A phase lasts as long as its slowest subsequence
+//  (286 tokens in 1,024 bits against a mean of 120), i.e. ~50 dependent instructions per token on a warp that runs
+//  alone on its scheduler; the look-up chain is not what it waits for.)
 struct BitWindow {
     const uint32_t *words;
     uint32_t widx, hi, lo, n1, q; // n1 = word widx + 2 (as loaded), q = word widx + 3 (as loaded, possibly still in flight)
