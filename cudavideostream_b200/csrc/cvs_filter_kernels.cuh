@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
     // fo[.][m] = (f[2m+1], f[2m+2]) -- tap j of output pair (o, o+1) reads (f[o+3j], f[o+3j+1]), which starts on an odd
     // float for odd j, and FFMA2 wants an aligned register pair.
     f32x2 fe[K][NE], fo[K][NO > 0 ? NO : 1];
-    auto load_row = [&](int rr, f32x2 (&de)[NE], f32x2 (&dO)[NO > 0 ? NO : 1]) {
-        uint32_t wd[NW];
+    // A warp issues in order and waits at the first instruction that reads a loaded register, so the words of a row are
+    // requested one output row before they are converted: fetch() only loads, convert() is the first reader.
+    auto fetch = [&](int rr, uint32_t (&wd)[NW]) {
 #pragma unroll
         for (int u = 0; u < NW; u++) {
             const int xi = xw + u - WL;
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
             if (rr >= 0 && rr < height && xi >= 0 && xi < wordsperrow)
                 wd[u] = __ldg(reinterpret_cast<const uint32_t *>(fin + (size_t)rr * rowbytes) + xi);
         }
+    };
+    auto convert = [&](const uint32_t (&wd)[NW], f32x2 (&de)[NE], f32x2 (&dO)[NO > 0 ? NO : 1]) {
 #pragma unroll
         for (int m = 0; m < NE; m++) {
             const int b0 = 4 * WL - HALO + 2 * m, b1 = b0 + 1; // byte indices inside wd[]
@@ -184,13 +187,21 @@ __global__ void __launch_bounds__(128) k_conv_strip(const uint8_t *__restrict__ 
             dO[m] = add2_bcast(pack2u(u0, u1), -8388608.0f);
         }
     };
+    {
+        uint32_t w0[K - 1][NW];
 #pragma unroll
-    for (int i = 0; i < K - 1; i++) load_row(row0 - R + i, fe[i], fo[i]);
+        for (int i = 0; i < K - 1; i++) fetch(row0 - R + i, w0[i]);
+#pragma unroll
+        for (int i = 0; i < K - 1; i++) convert(w0[i], fe[i], fo[i]);
+    }
+    uint32_t wn[NW]; // words of the next input row, in flight
+    fetch(row0 + R, wn);
 #pragma unroll
     for (int r = 0; r < kConvRows; r++) {
         const int row = row0 + r;
         if (row >= height) break;
-        load_row(row + R, fe[(r + K - 1) % K], fo[(r + K - 1) % K]);
+        convert(wn, fe[(r + K - 1) % K], fo[(r + K - 1) % K]);
+        if (r + 1 < kConvRows) fetch(row + 1 + R, wn);
         f32x2 acc[NB / 2];
 #pragma unroll
         for (int o = 0; o < NB / 2; o++) acc[o] = 0ull;
