@@ -42,13 +42,21 @@ CASES = [
     ("q95_420_8x8", 8, 8, [cv2.IMWRITE_JPEG_QUALITY, 95]),
     ("q95_420_3x5", 3, 5, [cv2.IMWRITE_JPEG_QUALITY, 95]),
     ("q92_420_1280x720", 1280, 720, [cv2.IMWRITE_JPEG_QUALITY, 92]),
+    ("q90_gray_123x77", 123, 77, [cv2.IMWRITE_JPEG_QUALITY, 90]),            # one component (encoded from a gray image)
+    ("q85_422_rst8_640x480", 640, 480, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+                                       cv2.IMWRITE_JPEG_RST_INTERVAL, 8]),
+    ("q30_444_rst3_97x55", 97, 55, [cv2.IMWRITE_JPEG_QUALITY, 30, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444,
+                                   cv2.IMWRITE_JPEG_RST_INTERVAL, 3]),
 ]
 
 
 def main():
     out = {}
     for i, (name, w, h, params) in enumerate(CASES):
-        ok, enc = cv2.imencode(".jpg", picture(w, h, 1000 + i), params)
+        pic = picture(w, h, 1000 + i)
+        if "_gray_" in name:
+            pic = np.ascontiguousarray(pic[:, :, 1])
+        ok, enc = cv2.imencode(".jpg", pic, params)
         assert ok
         dec = cv2.imdecode(enc, cv2.IMREAD_COLOR)
         assert dec.shape == (h, w, 3)

@@ -78,7 +78,7 @@ def test_other_samplings_qualities_and_sizes(cvs, oracle, monkeypatch, sub_bits)
         g = _decode(cvs, jpg, w, h)
         assert hashlib.sha256(g.tobytes()).digest() == z[n + "/sha"].tobytes(), n
         done += 1
-    assert done >= 13  # includes the two streams with restart intervals (k_entropy_restart)
+    assert done >= 16  # includes the streams with restart intervals (k_entropy_restart) and the one-component frame
 
 
 def test_restart_intervals_at_camera_size(cvs, oracle, monkeypatch):
