@@ -646,7 +646,10 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
         hb.append((b, len(j)))
     outs = [[(cvs.alloc_host(n + 32), cvs.alloc_host(4 * n + 32), (C.c_uint * 1)()) for _ in range(4)] for _ in range(nstreams)]
 
-    def run(k, ns, jpeg=True):
+    from cudavideostream_b200 import wire as wirefmt
+    wouts = [[cvs.alloc_host(wirefmt.bound(w, h) + 64) for _ in range(4)] for _ in range(nstreams)]
+
+    def run(k, ns, jpeg=True, wire=False):
         pend, d2h, h2d = [[] for _ in range(ns)], 0, 0
         for q in range(ns):
             streams[q].reset(raw[0].array()[:n])
@@ -657,8 +660,13 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
                 if len(pend[q]) == 4:
                     tk, pp = pend[q].pop(0)
                     s.wait(tk)
-                    d2h += 4 + 5 * pp[0]
-                if jpeg:
+                    d2h += wirefmt.size_of(pp.array()) if wire else 4 + 5 * pp[0]
+                if wire:
+                    b, nb = hb[(i + 1) % 2]
+                    h2d += nb
+                    wb = wouts[q][i % 4]
+                    pend[q].append((s.submit_jpeg_wire_raw(b.ptr, nb, wb.ptr, None, ""), wb))
+                elif jpeg:
                     b, nb = hb[(i + 1) % 2]
                     h2d += nb
                     pend[q].append((s.submit_jpeg_raw(b.ptr, nb, fb.ptr, None, "", C.addressof(pb), xb.ptr), pb))
@@ -668,15 +676,15 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
         for q in range(ns):
             for tk, pp in pend[q]:
                 streams[q].wait(tk)
-                d2h += 4 + 5 * pp[0]
+                d2h += wirefmt.size_of(pp.array()) if wire else 4 + 5 * pp[0]
         return h2d, d2h
 
-    def timed(k, ns, jpeg=True):  # whole job: frames of all ranks / max-over-ranks time
-        run(8, ns, jpeg)
+    def timed(k, ns, jpeg=True, wire=False):  # whole job: frames of all ranks / max-over-ranks time
+        run(8, ns, jpeg, wire)
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        h2d, d2h = run(k, ns, jpeg)
+        h2d, d2h = run(k, ns, jpeg, wire)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         dt, (nfr, h2d, d2h) = cvs.sharding.reduce_job(dt, [k * ns, h2d, d2h], torch.device("cuda", local))
@@ -685,11 +693,14 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
     v, h2d, d2h = timed(nframes, nstreams)
     v1, _, _ = timed(nframes, 1)
     vr, h2dr, _ = timed(nframes, nstreams, jpeg=False)
+    vw, h2dw, d2hw = timed(nframes, nstreams, wire=True)
     for s in streams:
         s.close()
     return {"value": v, "unit": "frames/s", "streams_per_gpu": nstreams, "frames_per_gpu": nframes * nstreams, "h2d_bytes": h2d,
             "d2h_bytes": d2h,
             "one_stream": v1, "same_frames_uploaded_raw": {"value": vr, "h2d_bytes": h2dr},
+            "jpeg_in_cvw1_out": {"value": vw, "h2d_bytes": h2dw, "d2h_bytes": d2hw,
+                                 "note": "cvs_submit_jpeg_wire: both opt-ins, the fewest bytes across PCIe in either direction"},
             "decoder": os.environ.get("CVS_JPEG_DECODER", "own (cvs_jpeg.cuh), nvJPEG for forms it does not cover"),
             "note": "the reference's camera frames f1.jpg / f2.jpg alternating (about 6 % of the bytes change) on every stream; "
                     "cvs_submit_jpeg decodes the bitstream on the device (hand-written kernels, pixels identical to OpenCV's), "

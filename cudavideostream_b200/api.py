@@ -75,6 +75,7 @@ SIGNATURES = {
     "cvs_wire_decode_device": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "cvs_wire_decode_status": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "cvs_submit_jpeg": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_char_p, _vp, _vp, C.POINTER(C.c_uint64)]),
+    "cvs_submit_jpeg_wire": (C.c_int, [_vp, _vp, _sz, _vp, _vp, C.c_char_p, C.POINTER(C.c_uint64)]),
     "cvs_decode_jpeg_device": (C.c_int, [_vp, _vp, _sz, _vp, _vp]),
     "cvs_synth_base_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint64, _vp]),
     "cvs_synth_next_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, _vp]),
@@ -198,6 +199,12 @@ class Stream:
         t = C.c_uint64(0)
         _check(load_library().cvs_submit_jpeg(self._h, jpeg_ptr, jpeg_bytes, diff_ptr, show_ptr, text.encode(), pos_ptr, xs_ptr,
                                               C.byref(t)))
+        return t.value
+
+    def submit_jpeg_wire_raw(self, jpeg_ptr: int, jpeg_bytes: int, wire_ptr: int, show_ptr, text: str) -> int:
+        """cvs_submit_jpeg_wire: JPEG bitstream in, one compact CVW1 frame out."""
+        t = C.c_uint64(0)
+        _check(load_library().cvs_submit_jpeg_wire(self._h, jpeg_ptr, jpeg_bytes, wire_ptr, show_ptr, text.encode(), C.byref(t)))
         return t.value
 
     def decode_jpeg_device(self, jpeg: bytes, d_out: int, cuda_stream: int = 0) -> None:

@@ -1290,6 +1290,13 @@ cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes,
     return submit_common(h, jpeg, diff_out, show, text, pos, xs, nullptr, ticket, jpeg_bytes);
 }
 
+cvs_status cvs_submit_jpeg_wire(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *wire_out, uint8_t *show,
+                                const char *text, uint64_t *ticket)
+{
+    if (!jpeg || jpeg_bytes == 0 || !wire_out) return fail(CVS_ERR_INVALID, "null argument");
+    return submit_common(h, jpeg, nullptr, show, text, nullptr, nullptr, wire_out, ticket, jpeg_bytes);
+}
+
 cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out, void *cuda_stream)
 {
     cvs_status st = check_handle(h);

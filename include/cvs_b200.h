@@ -254,6 +254,10 @@ cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int heig
  * --------------------------------------------------------------------------------------------------------------- */
 cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *diff_out, uint8_t *show,
                            const char *text, unsigned int *pos, int *xs, uint64_t *ticket);
+/* both opt-ins together: the camera's JPEG bitstream in, one compact CVW1 frame (cvs_submit_wire) out -- the fewest
+ * bytes across PCIe in either direction (1080p camera frame: 0.43 MB up, 16 + N/192 + 2*pos bytes down) */
+cvs_status cvs_submit_jpeg_wire(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *wire_out, uint8_t *show,
+                                const char *text, uint64_t *ticket);
 /* the decode alone: baseline JPEG of the stream's frame size -> BGR24 frame in device memory (N bytes) */
 cvs_status cvs_decode_jpeg_device(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *d_out,
                                   void *cuda_stream);

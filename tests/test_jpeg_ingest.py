@@ -160,6 +160,44 @@ def test_submit_jpeg_payload_is_the_oracles(cvs, oracle, monkeypatch):
     s.close()
 
 
+def test_jpeg_in_compact_wire_format_out(cvs, oracle, monkeypatch):
+    """Both opt-ins together (cvs_submit_jpeg_wire): the CVW1 frame holds the oracle's payload of the oracle's pixels."""
+    from cudavideostream_b200 import wire
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    w, h = 1920, 1080
+    n = 3 * w * h
+    j1, j2 = _jpeg("k1_f1.jpg"), _jpeg("k1_f2.jpg")
+    g1, g2 = oracle.jpeg_decode_bgr(j1).reshape(-1), oracle.jpeg_decode_bgr(j2).reshape(-1)
+    s = cvs.Stream(w, h, g1)
+    wout = cvs.alloc_host(wire.bound(w, h) + 64)
+    oref = g1
+    for cur, j in ((g2, j2), (g1, j1)):
+        jb = cvs.alloc_host(len(j) + 64)
+        jb.array()[:len(j)] = np.frombuffer(j, dtype=np.uint8)
+        s.wait(s.submit_jpeg_wire_raw(jb.ptr, len(j), wout.ptr, None, ""))
+        opos, oxs, odiff, oref, _ = oracle.diff_compact(cur, oref, 20)
+        enc = wout.array()
+        pos, xs, diff = wire.parse(enc[:wire.size_of(enc)])
+        assert pos == opos and np.array_equal(xs, oxs) and np.array_equal(diff, odiff)
+        assert wire.size_of(enc) < (4 + 5 * opos) // 2
+    assert np.array_equal(s.reference(), oref)
+    s.close()
+
+
+def test_camera_frame_3840x2160(cvs, oracle, monkeypatch):
+    """A 4K frame (13 k subsequences, four times the blocks): still OpenCV's pixels."""
+    cv2 = pytest.importorskip("cv2")
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    src = cv2.imdecode(np.frombuffer(_jpeg("k1_f2.jpg"), np.uint8), cv2.IMREAD_COLOR)
+    big = cv2.resize(src, (3840, 2160), interpolation=cv2.INTER_CUBIC)
+    ok, enc = cv2.imencode(".jpg", big, [cv2.IMWRITE_JPEG_QUALITY, 93])
+    assert ok
+    ref = cv2.imdecode(enc, cv2.IMREAD_COLOR).reshape(-1)
+    g = _decode(cvs, enc.tobytes(), 3840, 2160)
+    bad = np.flatnonzero(g != ref)
+    assert bad.size == 0, f"{bad.size} bytes differ, first at {bad[:5]}"
+
+
 def test_rejects_other_sizes_garbage_and_damaged_streams(cvs, monkeypatch):
     monkeypatch.setenv("CVS_JPEG_DECODER", "own")
     w, h = 640, 360
