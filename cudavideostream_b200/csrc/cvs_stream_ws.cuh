@@ -351,7 +351,10 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
                             if ((uint32_t)px < npx) {
                                 uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
                                 if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
+#ifndef CVS_EXP_NO_HIST // (timing experiment: the atomics are 0.68 of mode 5's 7.87 us per frame; the weighted gray of
+                        //  32 pixels per thread, ~15 instructions each, is what mode 5 costs over mode 0)
                                 atomicAdd(&shist[gv * kWsHistCopies + (lane & (kWsHistCopies - 1))], 1u); // server.cpp:103-106
+#endif
                             }
                         }
                     }
