@@ -1367,7 +1367,9 @@ cvs_status cvs_wait(cvs_handle h, uint64_t ticket)
                 (unsigned long long)ticket, t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3, t[4] * 1e3, t[5] * 1e3, n,
                 s.pushed ? "push" : (s.spec ? "spec" : "copy"));
     }
-    return CVS_OK;
+    // a capacity overflow or a damaged JPEG bitstream: the ticket is consumed and whatever the frame produced has been
+    // delivered, but the caller must know (after a damaged frame the reference holds its pixels: cvs_reset re-seeds it)
+    return st;
 }
 
 cvs_status cvs_exec(cvs_handle h, uint8_t *frame, uint8_t *show, const char *text, unsigned int *pos, int *xs)

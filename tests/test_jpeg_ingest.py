@@ -218,6 +218,26 @@ def test_rejects_other_sizes_garbage_and_damaged_streams(cvs, monkeypatch):
     pos, xs, diff, _ = s.exec(f)
     assert pos == n
     s.close()
+    # a truncated frame through the pipelined call: cvs_wait reports it (the stream holds fewer blocks than the image)
+    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    name = "q50_420_641x359"
+    w, h = (int(v) for v in z[name + "/wh"])
+    n = 3 * w * h
+    good = z[name + "/jpg"].tobytes()
+    cutj = good[:len(good) // 2] + b"\xff\xd9"
+    s = cvs.Stream(w, h, np.zeros(n, dtype=np.uint8))
+    jb = cvs.alloc_host(len(good) + 64)
+    dout, xout, pb = cvs.alloc_host(n + 32), cvs.alloc_host(4 * n + 32), (C.c_uint * 1)()
+    jb.array()[:len(cutj)] = np.frombuffer(cutj, dtype=np.uint8)
+    tk = s.submit_jpeg_raw(jb.ptr, len(cutj), dout.ptr, None, "", C.addressof(pb), xout.ptr)
+    with pytest.raises(cvs.CVSError) as e:
+        s.wait(tk)
+    assert e.value.status == 1
+    s.reset(np.zeros(n, dtype=np.uint8))  # the damaged frame's pixels went into the reference: re-seed it
+    jb.array()[:len(good)] = np.frombuffer(good, dtype=np.uint8)
+    s.wait(s.submit_jpeg_raw(jb.ptr, len(good), dout.ptr, None, "", C.addressof(pb), xout.ptr))
+    assert hashlib.sha256(s.reference().tobytes()).digest() != b"" and pb[0] > 0
+    s.close()
     # a damaged entropy-coded segment: never a crash, a hang or a write outside the frame; either an error status or a picture
     rng = np.random.default_rng(5)
     z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
