@@ -174,7 +174,7 @@ struct JpegDecoder {
     std::vector<uint8_t> header;   // ... and its bytes up to the scan (a camera repeats them: no table rebuild per frame)
     cvs::jpg::Tables tables_host;  // what d_tables holds
     bool tables_valid = false;
-    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr;
+    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr, *d_hw = nullptr;
     uint8_t *d_hmap = nullptr;
     uint32_t *d_mid_state = nullptr, *d_mid_nblk = nullptr;
     int32_t *d_mid_dc = nullptr;
@@ -1019,6 +1019,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
                      o_nblk = carve(nsub_cap * sizeof(uint32_t)), o_dcs = carve(3 * nsub_cap * sizeof(int32_t)),
                      o_tile_blk = carve(ntile_cap * sizeof(uint32_t)), o_tile_dc = carve(3 * ntile_cap * sizeof(int32_t)),
                      o_hx = carve(6 * nsub_cap * sizeof(uint32_t)), o_hy = carve(6 * nsub_cap * sizeof(uint32_t)),
+                     o_hw = carve(6 * nsub_cap * sizeof(uint32_t)),
                      o_hmap = carve(16 * nsub_cap), o_mid_state = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
                      o_mid_nblk = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
                      o_mid_dc = carve(3 * J::kMaxSplit * nsub_cap * sizeof(int32_t)), o_planes = carve(block_cap * 64 + 256);
@@ -1043,6 +1044,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
         jd.d_tile_dc = reinterpret_cast<int32_t *>(a + o_tile_dc);
         jd.d_hx = reinterpret_cast<uint32_t *>(a + o_hx);
         jd.d_hy = reinterpret_cast<uint32_t *>(a + o_hy);
+        jd.d_hw = reinterpret_cast<uint32_t *>(a + o_hw);
         jd.d_hmap = a + o_hmap;
         jd.d_mid_state = reinterpret_cast<uint32_t *>(a + o_mid_state);
         jd.d_mid_nblk = reinterpret_cast<uint32_t *>(a + o_mid_nblk);
@@ -1112,6 +1114,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
     ep.mid.dc = jd.d_mid_dc;
     ep.hx = jd.d_hx;
     ep.hy = jd.d_hy;
+    ep.hw = jd.d_hw;
     ep.hmap = jd.d_hmap;
     ep.hypotheses = jd.hypotheses ? 1u : 0u;
     ep.changed = jd.d_changed;

@@ -513,7 +513,7 @@ struct EntropyParams {
     uint32_t *tile_blk;       // [ntiles] per-tile totals
     int32_t *tile_dc;         // [3][ntiles]
     MidRecords mid;           // inner-boundary records of the counting runs (write pass granularity)
-    uint32_t *hx, *hy;        // [nsub_max * bpm] exit states of the phase hypotheses: fresh / followed one subsequence further
+    uint32_t *hx, *hy, *hw;   // [nsub_max * bpm] exit states of the phase hypotheses: fresh / followed one / two subsequences further
     uint8_t *hmap;            // [nsub_max][16] successor of candidate c of boundary i-1 among the candidates of boundary i
     uint32_t hypotheses;      // 0: plain rounds from the guess "a block starts here" (A/B measurements)
     unsigned int *changed;    // [kMaxRounds] states changed per round
@@ -559,21 +559,24 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     if (p.hypotheses) {
         const uint32_t B = (uint32_t)g.bpm, nh = nsub * B, gstride = gridDim.x * kEntropyThreads;
         const uint32_t first = blockIdx.x * kEntropyThreads + tid;
-        // X: a block of phase h starts at the subsequence boundary
+        // X: a block of phase h starts at the subsequence boundary; Y, W: that sequence followed through the next and the
+        // next-but-one subsequence.  One thread walks the three in a row -- nobody else's result is needed in between, so
+        // there is no grid barrier between them, and a thread waits for the tokens of ITS three subsequences (at most
+        // 600 on the camera frame) instead of three times for the slowest subsequence of the frame (3 x 286).
         for (uint32_t idx = first; idx < nh; idx += gstride) {
             const uint32_t i = idx / B, h = idx - i * B;
-            p.hx[idx] = run_subsequence<false>(tbr, g, p.words, T, i, pack_state(0, h, 0), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            const uint32_t x = run_subsequence<false>(tbr, g, p.words, T, i, pack_state(0, h, 0), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            p.hx[idx] = x;
+            if (i == 0) p.hy[idx] = kStateUnset;
+            if (i + 1 < nsub) {
+                const uint32_t y = run_subsequence<false>(tbr, g, p.words, T, i + 1, x, s_nat, nullptr, 0, 0, 0, 0).exit_state;
+                p.hy[idx + B] = y;
+                if (i + 2 < nsub)
+                    p.hw[idx + 2 * B] = run_subsequence<false>(tbr, g, p.words, T, i + 2, y, s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            }
         }
         grid.sync();
-        // Y: the X sequences of the subsequence in front, followed through this one
-        for (uint32_t idx = first; idx < nh; idx += gstride) {
-            const uint32_t i = idx / B;
-            uint32_t y = kStateUnset;
-            if (i) y = run_subsequence<false>(tbr, g, p.words, T, i, __ldcg(p.hx + idx - B), s_nat, nullptr, 0, 0, 0, 0).exit_state;
-            p.hy[idx] = y;
-        }
-        grid.sync();
-        // W: the Y sequences followed once more; where does each candidate of boundary i-1 arrive among those of boundary i?
+        // where does each candidate of boundary i-1 arrive among those of boundary i?
         for (uint32_t idx = first; idx < nh; idx += gstride) {
             const uint32_t i = idx / B, h = idx - i * B;
             uint32_t m0 = kNoCandidate, m1 = kNoCandidate;
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
                         break;
                     }
                 if (i >= 2) {
-                    const uint32_t w = run_subsequence<false>(tbr, g, p.words, T, i, __ldcg(p.hy + idx - B), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+                    const uint32_t w = __ldcg(p.hw + idx); // candidate Y_h of the boundary in front, followed through subsequence i
                     for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
                         if (__ldcg(p.hx + i * B + h2) == w) m1 = h2;
                     for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
