@@ -781,6 +781,10 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         }
     }
     grid.sync();
+    if (trace) {
+        printf("prefix sums: %llu ns\n", jpg_now_ns() - t_prev);
+        t_prev = jpg_now_ns();
+    }
     // ---- write pass: one thread per G bits, from the states the counting runs left at the inner boundaries
     {
         Geometry gw = g;
@@ -801,7 +805,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
             run_subsequence<true>(tbr, gw, p.words, T, j, e, s_nat, p.coef, blk0, d0, d1, d2);
         }
     }
-    if (trace) printf("scan + write: %llu ns\n", jpg_now_ns() - t_prev);
+    if (trace) printf("write pass (block 0): %llu ns\n", jpg_now_ns() - t_prev);
     // the string must hold exactly the image's blocks (padding bits after the last block decode to no complete block
     // in a well-formed stream; more or fewer blocks means a damaged frame)
     if (total_blocks_seen && total_blocks_seen < g.nblocks) atomicOr(p.status, kJpegBlockCount);

@@ -249,7 +249,7 @@ cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int heig
  *   A damaged entropy-coded segment never writes outside the frame; when the decoder notices (the stream holds
  *   fewer blocks than the image, or the parallel decode does not settle) cvs_wait / cvs_sequence_status return
  *   CVS_ERR_INVALID for that frame.
- *   1080p camera frame (432 KB): 0.32 ms per decode on one stream, ~10,000 decodes/s with four streams of a GPU
+ *   1080p camera frame (432 KB): 0.30 ms per decode on one stream, ~11,000 decodes/s with four streams of a GPU
  *   (nvJPEG on the same box: 205/s) -- profiles/README.md.
  * --------------------------------------------------------------------------------------------------------------- */
 cvs_status cvs_submit_jpeg(cvs_handle h, const uint8_t *jpeg, size_t jpeg_bytes, uint8_t *diff_out, uint8_t *show,
