@@ -1065,13 +1065,14 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
     // ---- the entropy-coded segment crosses PCIe (0.4 MB instead of the 6.2 MB frame), FF 00 -> FF
     const uint32_t raw_len = (uint32_t)P.scan_bytes;
     CU_TRY(cudaMemcpyAsync(jd.d_raw, jpeg + P.scan_offset, raw_len, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(jd.d_arena, 0, jd.zero_bytes_fixed + (size_t)g.nblocks * 64 * sizeof(int16_t), st));
     const uint32_t ublocks = (raw_len + J::kUnstuffThreads * J::kUnstuffBytes - 1) / (J::kUnstuffThreads * J::kUnstuffBytes);
-    J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks);
-    J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks, jd.d_unst,
-                                                                 jd.d_total_bits, jd.d_seg_start, jd.seg_cap, jd.d_total_marks);
 
     if (P.restart_interval) {
+        // ---- scratch cleared, FF 00 -> FF and FF Dn dropped (launches of their own on this path)
+        CU_TRY(cudaMemsetAsync(jd.d_arena, 0, jd.zero_bytes_fixed + (size_t)g.nblocks * 64 * sizeof(int16_t), st));
+        J::k_unstuff_count<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks);
+        J::k_unstuff_write<<<ublocks, J::kUnstuffThreads, 0, st>>>(jd.d_raw, raw_len, jd.d_block_kept, jd.d_block_marks, jd.d_unst,
+                                                                     jd.d_total_bits, jd.d_seg_start, jd.seg_cap, jd.d_total_marks);
         // ---- Huffman decode of a scan with restart intervals: one thread per interval (k_entropy_restart)
         J::RestartParams rp;
         rp.tables = jd.d_tables;
@@ -1088,13 +1089,23 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
         if (rp.nseg + 1 > jd.seg_cap) return fail(CVS_ERR_INTERNAL, "restart interval table too small");
         J::k_entropy_restart<<<(rp.nseg + 127) / 128, 128, 0, st>>>(rp);
     } else {
-    // ---- Huffman decode: one cooperative launch (sync rounds, prefix sums, coefficient write)
+    // ---- one cooperative launch: scratch cleared, FF 00 -> FF, Huffman decode (hypotheses, rounds, prefix sums, write)
     // (entry states start as zero = "a block of phase 0 starts here": the first guess when the hypotheses are switched off)
     if (!jd.coop_blocks_per_sm) {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&jd.coop_blocks_per_sm, J::k_entropy, J::kEntropyThreads, 0));
         if (jd.coop_blocks_per_sm < 1) return fail(CVS_ERR_INTERNAL, "k_entropy does not fit an SM");
     }
     J::EntropyParams ep;
+    ep.raw = jd.d_raw;
+    ep.raw_len = raw_len;
+    ep.unst = jd.d_unst;
+    ep.unst_bytes = (uint32_t)std::min(jd.raw_cap, round_up(raw_len, 4096) + 4096);
+    ep.block_kept = jd.d_block_kept;
+    ep.block_marks = jd.d_block_marks;
+    ep.total_marks_out = jd.d_total_marks;
+    ep.seg_start = jd.d_seg_start;
+    ep.seg_cap = jd.seg_cap;
+    ep.total_bits_out = jd.d_total_bits;
     ep.tables = jd.d_tables;
     ep.g = g;
     ep.words = reinterpret_cast<const uint32_t *>(jd.d_unst);

@@ -360,11 +360,11 @@ __device__ __forceinline__ uint32_t unstuff_keep_mask(const uint8_t *raw, uint32
     return keep;
 }
 
-__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_count(const uint8_t *__restrict__ raw, uint32_t raw_len, uint32_t *block_kept,
-                                                                  uint32_t *block_marks)
+// one block's share (block index vb of the unstuffing grid); kUnstuffThreads threads
+__device__ __forceinline__ void unstuff_count_block(uint32_t vb, const uint8_t *__restrict__ raw, uint32_t raw_len, uint32_t *block_kept,
+                                                    uint32_t *block_marks, uint32_t (*wsum)[kUnstuffThreads / 32])
 {
-    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
-    const uint32_t first = (blockIdx.x * kUnstuffThreads + threadIdx.x) * kUnstuffBytes;
+    const uint32_t first = (vb * kUnstuffThreads + threadIdx.x) * kUnstuffBytes;
     uint8_t b[kUnstuffBytes];
     uint32_t mk = 0;
     uint32_t n = first < raw_len ? (uint32_t)__popc(unstuff_keep_mask(raw, raw_len, first, b, &mk)) : 0u;
@@ -378,27 +378,25 @@ __global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_count(const uint8_t
     if (threadIdx.x < 2) {
         uint32_t t = 0;
         for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[threadIdx.x][w];
-        (threadIdx.x ? block_marks : block_kept)[blockIdx.x] = t;
+        (threadIdx.x ? block_marks : block_kept)[vb] = t;
     }
+    __syncthreads();
 }
 
 // out must be zero beyond the string (the decoder looks up to 16 bytes past its end); total_bits <- 8 * kept bytes;
 // seg_start[m] <- byte offset (in out) at which restart interval m starts (seg_start[0] = 0 is the caller's),
 // total_marks <- number of restart markers
-__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t *__restrict__ raw, uint32_t raw_len,
-                                                                  const uint32_t *__restrict__ block_kept,
-                                                                  const uint32_t *__restrict__ block_marks, uint8_t *out,
-                                                                  uint32_t *total_bits, uint32_t *seg_start, uint32_t seg_cap,
-                                                                  uint32_t *total_marks)
+__device__ __forceinline__ void unstuff_write_block(uint32_t vb, uint32_t nvb, const uint8_t *__restrict__ raw, uint32_t raw_len,
+                                                    const uint32_t *block_kept, const uint32_t *block_marks, uint8_t *out,
+                                                    uint32_t *total_bits, uint32_t *seg_start, uint32_t seg_cap, uint32_t *total_marks,
+                                                    uint32_t (*wsum)[kUnstuffThreads / 32], uint32_t *s_base)
 {
-    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
-    __shared__ uint32_t s_base[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // bytes kept / markers seen by the blocks in front of this one
     uint32_t part = 0, partm = 0;
-    for (uint32_t j = tid; j < blockIdx.x; j += kUnstuffThreads) {
-        part += block_kept[j];
-        partm += block_marks[j];
+    for (uint32_t j = tid; j < vb; j += kUnstuffThreads) {
+        part += __ldcg(block_kept + j);
+        partm += __ldcg(block_marks + j);
     }
     part = __reduce_add_sync(0xffffffffu, part);
     partm = __reduce_add_sync(0xffffffffu, partm);
@@ -415,7 +413,7 @@ __global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t
     __syncthreads();
     const uint32_t base = s_base[0], basem = s_base[1];
     __syncthreads();
-    const uint32_t first = (blockIdx.x * kUnstuffThreads + tid) * kUnstuffBytes;
+    const uint32_t first = (vb * kUnstuffThreads + tid) * kUnstuffBytes;
     uint8_t b[kUnstuffBytes];
     uint32_t mk = 0;
     const uint32_t keep = first < raw_len ? unstuff_keep_mask(raw, raw_len, first, b, &mk) : 0u;
@@ -448,12 +446,33 @@ __global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t
             }
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && tid == kUnstuffThreads - 1) {
+    if (vb == nvb - 1 && tid == kUnstuffThreads - 1) {
         uint32_t t = 0;
         for (int w = 0; w < kUnstuffThreads / 32; w++) t += wsum[0][w];
         *total_bits = 8u * (base + (t & 0xffffu));
         *total_marks = basem + (t >> 16);
     }
+    __syncthreads();
+}
+
+// stand-alone launches (scans with restart intervals; k_entropy does the same work in its own first phases)
+__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_count(const uint8_t *__restrict__ raw, uint32_t raw_len, uint32_t *block_kept,
+                                                                  uint32_t *block_marks)
+{
+    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
+    unstuff_count_block(blockIdx.x, raw, raw_len, block_kept, block_marks, wsum);
+}
+
+__global__ void __launch_bounds__(kUnstuffThreads) k_unstuff_write(const uint8_t *__restrict__ raw, uint32_t raw_len,
+                                                                  const uint32_t *__restrict__ block_kept,
+                                                                  const uint32_t *__restrict__ block_marks, uint8_t *out,
+                                                                  uint32_t *total_bits, uint32_t *seg_start, uint32_t seg_cap,
+                                                                  uint32_t *total_marks)
+{
+    __shared__ uint32_t wsum[2][kUnstuffThreads / 32];
+    __shared__ uint32_t s_base[2];
+    unstuff_write_block(blockIdx.x, gridDim.x, raw, raw_len, block_kept, block_marks, out, total_bits, seg_start, seg_cap, total_marks,
+                        wsum, s_base);
 }
 
 // ---- entropy decode, scans with restart intervals: every interval starts byte-aligned in a known state (first block of
@@ -502,6 +521,14 @@ __global__ void __launch_bounds__(128) k_entropy_restart(const RestartParams p)
 
 // ---- entropy decode -------------------------------------------------------------------------------------------------
 struct EntropyParams {
+    // first phases: clear the scratch, FF 00 -> FF (what k_unstuff_count / k_unstuff_write do as launches of their own)
+    const uint8_t *raw;       // entropy-coded segment as received
+    uint32_t raw_len;
+    uint8_t *unst;            // unstuffed string (= words)
+    uint32_t unst_bytes;      // bytes of it to clear (a multiple of 16, covers the string and its padding)
+    uint32_t *block_kept, *block_marks, *total_marks_out, *seg_start;
+    uint32_t seg_cap;
+    uint32_t *total_bits_out;
     const Tables *tables;     // device copy
     Geometry g;
     const uint32_t *words;    // unstuffed string
@@ -548,12 +575,37 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     __syncthreads();
     const TableRef tbr = table_ref(&tb);
     const Geometry g = p.g;
-    const uint32_t T = *p.total_bits;
-    const uint32_t nsub = (T + g.sub_bits - 1) / g.sub_bits; // <= nsub_max
-    const uint32_t ntiles = (nsub + kEntropyThreads - 1) / kEntropyThreads;
-
     const bool trace = p.debug && blockIdx.x == 0 && tid == 0;
     unsigned long long t_prev = trace ? jpg_now_ns() : 0ull;
+
+    // ---- clear what must start as zero (round counters, entry states, coefficients, the unstuffed string's buffer) and
+    //      count the bytes that stay; then compact them.  Two grid barriers instead of a memset and two launches.
+    {
+        static_assert(kUnstuffThreads == kEntropyThreads, "the unstuffing phases run on k_entropy's blocks");
+        uint32_t(*wsum)[kUnstuffThreads / 32] = reinterpret_cast<uint32_t(*)[kUnstuffThreads / 32]>(&s_scan[0][0]);
+        const uint32_t gthreads = gridDim.x * kEntropyThreads, gtid = blockIdx.x * kEntropyThreads + tid;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        uint4 *cz = reinterpret_cast<uint4 *>(p.coef);
+        for (uint32_t j = gtid; j < g.nblocks * 8u; j += gthreads) cz[j] = z; // 128 bytes per block
+        uint4 *uz = reinterpret_cast<uint4 *>(p.unst);
+        for (uint32_t j = gtid; j < p.unst_bytes / 16u; j += gthreads) uz[j] = z;
+        for (uint32_t j = gtid; j < g.nsub_max + 2u; j += gthreads) p.entry[j] = 0u; // first guess: a block of phase 0 starts here
+        for (uint32_t j = gtid; j < (uint32_t)kMaxRounds; j += gthreads) p.changed[j] = 0u;
+        const uint32_t nvb = (p.raw_len + kUnstuffThreads * kUnstuffBytes - 1) / (kUnstuffThreads * kUnstuffBytes);
+        for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x) unstuff_count_block(vb, p.raw, p.raw_len, p.block_kept, p.block_marks, wsum);
+        grid.sync();
+        for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+            unstuff_write_block(vb, nvb, p.raw, p.raw_len, p.block_kept, p.block_marks, p.unst, p.total_bits_out, p.seg_start, p.seg_cap,
+                                p.total_marks_out, wsum, s_tile_base);
+        grid.sync();
+        if (trace) {
+            printf("clear + unstuff: %llu ns\n", jpg_now_ns() - t_prev);
+            t_prev = jpg_now_ns();
+        }
+    }
+    const uint32_t T = __ldcg(p.total_bits);
+    const uint32_t nsub = (T + g.sub_bits - 1) / g.sub_bits; // <= nsub_max
+    const uint32_t ntiles = (nsub + kEntropyThreads - 1) / kEntropyThreads;
 
     // ---- phase hypotheses (see the header): seed entry[] with the states the true token sequence passes through
     if (p.hypotheses) {
