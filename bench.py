@@ -696,7 +696,24 @@ def jpeg_leg(cvs, torch, local, nframes, nstreams=3, barrier=lambda: None):
     vw, h2dw, d2hw = timed(nframes, nstreams, wire=True)
     for s in streams:
         s.close()
-    return {"value": v, "unit": "frames/s", "streams_per_gpu": nstreams, "frames_per_gpu": nframes * nstreams, "h2d_bytes": h2d,
+    # what the reference does with the same bitstreams: OpenCV (libjpeg-turbo) on one host thread, as its capture
+    # thread runs it (server/src/threads.cpp:32-41, :118)
+    ref_cpu = None
+    try:
+        import cv2
+        bufs = [np.frombuffer(j, dtype=np.uint8) for j in jpgs]
+        cv2.imdecode(bufs[0], cv2.IMREAD_COLOR)
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 1.0:
+            cv2.imdecode(bufs[k & 1], cv2.IMREAD_COLOR)
+            k += 1
+        ms = 1e3 * (time.perf_counter() - t0) / k
+        ref_cpu = {"opencv_imdecode_ms_per_frame": ms, "frames_per_s_one_thread": 1e3 / ms,
+                   "what": "cv2.imdecode of the same two bitstreams on one host thread (the reference's capture-side decode); "
+                           "same pixels as the GPU decoder, bit for bit"}
+    except Exception as e:  # no OpenCV on the box
+        ref_cpu = {"unavailable": str(e)[:120]}
+    return {"value": v, "unit": "frames/s", "streams_per_gpu": nstreams, "reference_cpu_decode": ref_cpu, "frames_per_gpu": nframes * nstreams, "h2d_bytes": h2d,
             "d2h_bytes": d2h,
             "one_stream": v1, "same_frames_uploaded_raw": {"value": vr, "h2d_bytes": h2dr},
             "jpeg_in_cvw1_out": {"value": vw, "h2d_bytes": h2dw, "d2h_bytes": d2hw,
