@@ -260,3 +260,44 @@ def test_rejects_other_sizes_garbage_and_damaged_streams(cvs, monkeypatch):
             assert g.size == 3 * w * h
         except cvs.CVSError as e:
             assert e.status == 1
+
+
+def test_random_streams_against_opencv(cvs, oracle, monkeypatch):
+    """Random pictures (smooth, noisy, saturated), sizes, qualities 3..100, samplings, optimised Huffman tables (unusual code
+    length distributions: the second-level tables and the canonical slow path of the decoder's look-up) and restart
+    intervals, encoded by OpenCV on the spot: the GPU decoder, the oracle and cv2.imdecode must agree bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    rng = np.random.default_rng(20261018)
+    samplings = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]
+    for case in range(28):
+        w, h = int(rng.integers(1, 420)), int(rng.integers(1, 300))
+        kind = case % 4
+        yy, xx = np.mgrid[0:h, 0:w]
+        if kind == 0:      # smooth
+            img = np.stack([(xx * 3 + yy) % 256, (yy * 5) % 256, (xx + yy * 2) % 256], axis=2)
+        elif kind == 1:    # noise: large coefficients, long codes
+            img = rng.integers(0, 256, size=(h, w, 3))
+        elif kind == 2:    # saturated rectangles on noise
+            img = rng.integers(100, 156, size=(h, w, 3))
+            for _ in range(5):
+                x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+                img[y0:y0 + h // 3 + 1, x0:x0 + w // 3 + 1] = rng.integers(0, 2, size=3) * 255
+        else:              # flat
+            img = np.full((h, w, 3), int(rng.integers(0, 256)))
+        img = img.astype(np.uint8)
+        gray = case % 7 == 3
+        params = [cv2.IMWRITE_JPEG_QUALITY, int(rng.integers(3, 101))]
+        if not gray:
+            params += [cv2.IMWRITE_JPEG_SAMPLING_FACTOR, samplings[int(rng.integers(0, 3))]]
+        if rng.integers(0, 2):
+            params += [cv2.IMWRITE_JPEG_OPTIMIZE, 1]
+        if case % 3 == 2:
+            params += [cv2.IMWRITE_JPEG_RST_INTERVAL, int(rng.integers(1, 9))]
+        ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(img[:, :, 1]) if gray else img, params)
+        assert ok
+        ref = cv2.imdecode(enc, cv2.IMREAD_COLOR).reshape(-1)
+        assert np.array_equal(oracle.jpeg_decode_bgr(enc.tobytes()).reshape(-1), ref), f"case {case}: oracle vs cv2 ({w}x{h}, {params})"
+        g = _decode(cvs, enc.tobytes(), w, h)
+        bad = np.flatnonzero(g != ref)
+        assert bad.size == 0, f"case {case} ({w}x{h}, {params}): {bad.size} bytes differ, first at {bad[:5]}"
