@@ -1010,7 +1010,7 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
             off += round_up(bytes, 256);
             return o;
         };
-        const size_t o_changed = carve(J::kMaxRounds * sizeof(unsigned int)), o_entry = carve((nsub_cap + 2) * sizeof(uint32_t)),
+        const size_t o_changed = carve(J::kRoundCounters * sizeof(unsigned int)), o_entry = carve((nsub_cap + 2) * sizeof(uint32_t)),
                      o_unst = carve(raw_cap), o_coef = carve(block_cap * 64 * sizeof(int16_t));
         jd.zero_bytes_fixed = o_coef; // + nblocks * 128 of the coefficients
         const size_t o_raw = carve(raw_cap), o_kept = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),

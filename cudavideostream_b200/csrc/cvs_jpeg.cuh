@@ -41,7 +41,7 @@ constexpr int kLutBits = 9;      // first-level look-ahead
 constexpr int kLut2Bits = 7;     // second level: the remaining bits of a 16-bit code
 constexpr int kLut2Tables = 8;   // second-level tables per Huffman table (the standard tables need 5)
 constexpr int kMaxSplit = 8;     // write-pass threads per subsequence
-constexpr int kMaxRounds = 4096; // rounds before the decode is declared failed (a camera frame needs one)
+constexpr int kRoundCounters = 4; // per-round change counters in rotation (see k_entropy)
 
 // Canonical Huffman table as the decoder wants it.  A decoded token is one 32-bit entry:
 //   bits 0-7 symbol (run << 4 | size), 8-12 code length, 13-18 token length (code + size bits),
@@ -543,7 +543,7 @@ struct EntropyParams {
     uint32_t *hx, *hy, *hw;   // [nsub_max * bpm] exit states of the phase hypotheses: fresh / followed one / two subsequences further
     uint8_t *hmap;            // [nsub_max][16] successor of candidate c of boundary i-1 among the candidates of boundary i
     uint32_t hypotheses;      // 0: plain rounds from the guess "a block starts here" (A/B measurements)
-    unsigned int *changed;    // [kMaxRounds] states changed per round
+    unsigned int *changed;    // [kRoundCounters] states changed in a round, three counters in rotation
     int16_t *coef;            // [nblocks][64], zeroed
     unsigned int *status;
     uint32_t debug;           // CVS_JPEG_TRACE=1: block 0 prints the time of every phase (measurements)
@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         uint4 *uz = reinterpret_cast<uint4 *>(p.unst);
         for (uint32_t j = gtid; j < p.unst_bytes / 16u; j += gthreads) uz[j] = z;
         for (uint32_t j = gtid; j < g.nsub_max + 2u; j += gthreads) p.entry[j] = 0u; // first guess: a block of phase 0 starts here
-        for (uint32_t j = gtid; j < (uint32_t)kMaxRounds; j += gthreads) p.changed[j] = 0u;
+        if (gtid < (uint32_t)kRoundCounters) p.changed[gtid] = 0u;
         const uint32_t nvb = (p.raw_len + kUnstuffThreads * kUnstuffBytes - 1) / (kUnstuffThreads * kUnstuffBytes);
         for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x) unstuff_count_block(vb, p.raw, p.raw_len, p.block_kept, p.block_marks, wsum);
         grid.sync();
@@ -711,7 +711,13 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     //      so this round could go -- makes those phases 183 us instead of 123 us with six times the records to store;
     //      317 us per frame either way.)
     bool converged = false;
-    for (uint32_t round = 0; round < (uint32_t)kMaxRounds; round++) {
+    // Exact states travel at least one subsequence per round, so nsub rounds always suffice (a stream whose codes do not
+    // self-synchronise at all -- every code equally long -- needs them all; a camera frame needs one).  The counter of a
+    // round is one of three in rotation: the one of round r + 1 is cleared during round r, when every thread has long
+    // read it for round r - 2.
+    for (uint32_t round = 0; round <= nsub; round++) {
+        unsigned int *const counter = p.changed + round % 3u;
+        if (blockIdx.x == 0 && tid == 0) p.changed[(round + 1u) % 3u] = 0u;
         for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const uint32_t i = tile * kEntropyThreads + tid;
             if (i >= nsub) continue;
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
             p.dcs[2 * g.nsub_max + i] = r.dc2;
             if (__ldcg(p.entry + i + 1) != r.exit_state) {
                 __stcg(p.entry + i + 1, r.exit_state);
-                if (i + 1 < nsub) atomicAdd(p.changed + round, 1u);
+                if (i + 1 < nsub) atomicAdd(counter, 1u);
             }
         }
         const unsigned long long t_run = trace ? jpg_now_ns() : 0ull;
@@ -733,10 +739,10 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         if (trace) {
             const unsigned long long t_now = jpg_now_ns();
             printf("round %u: run %llu ns, barrier %llu ns, %u states changed\n", round, t_run - t_prev, t_now - t_run,
-                   __ldcg(p.changed + round));
+                   __ldcg(counter));
             t_prev = t_now;
         }
-        if (__ldcg(p.changed + round) == 0) {
+        if (__ldcg(counter) == 0) {
             converged = true;
             break;
         }

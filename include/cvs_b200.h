@@ -247,8 +247,9 @@ cvs_status cvs_wire_decode_status(const uint32_t *d_scratch, int width, int heig
  *   are close to but not identical with libjpeg-turbo's (<= 5 apart on the fixture frames); CVS_JPEG_DECODER=own
  *   refuses them instead, CVS_JPEG_DECODER=nvjpeg sends everything there (measurements).
  *   A damaged entropy-coded segment never writes outside the frame; when the decoder notices (the stream holds
- *   fewer blocks than the image, or the parallel decode does not settle) cvs_wait / cvs_sequence_status return
- *   CVS_ERR_INVALID for that frame.
+ *   fewer blocks than the image) cvs_wait / cvs_sequence_status return CVS_ERR_INVALID for that frame.  Every
+ *   well-formed stream decodes, however unfriendly its code: the parallel decode falls back to as many rounds as it
+ *   needs (a stream whose codes are all equally long does not self-synchronise and decodes at sequential speed).
  *   1080p camera frame (432 KB): 0.30 ms per decode on one stream, ~11,000 decodes/s with four streams of a GPU
  *   (nvJPEG on the same box: 205/s) -- profiles/README.md.
  * --------------------------------------------------------------------------------------------------------------- */

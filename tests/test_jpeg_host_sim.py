@@ -71,3 +71,23 @@ def test_frame_without_huffman_tables(sim, oracle, tmp_path):
     rc, log, out = _run(sim, jp, 1024, tmp_path)
     assert rc == 0, log
     assert np.array_equal(np.fromfile(out, dtype=np.int16).reshape(-1, 64), oracle.jpeg_coefficients(bare))
+
+
+@pytest.mark.parametrize("name,dc_len,ac_len", [("q95_420_200x150", 11, 10), ("q90_gray_123x77", 10, 12), ("q90_422_320x240", 16, 16),
+                                                ("q85_444_161x97", 4, 9)])
+def test_uniform_long_codes(sim, oracle, tmp_path, name, dc_len, ac_len):
+    """The same coefficients re-encoded with Huffman tables whose codes are all dc_len / ac_len bits long: dozens of long
+    prefixes -- more than the decoder has second-level tables, so the canonical slow path decodes most tokens."""
+    from util import transcode_huffman
+    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    jpg = z[name + "/jpg"].tobytes()
+    info, coef = oracle.jpeg_info(jpg), oracle.jpeg_coefficients(jpg)
+    t = transcode_huffman(jpg, coef, info["hs"], info["vs"], info["ncomp"], dc_len, ac_len)
+    assert np.array_equal(oracle.jpeg_coefficients(t), coef)  # the transcoder itself
+    jp = str(tmp_path / "t.jpg")
+    with open(jp, "wb") as f:
+        f.write(t)
+    for sub_bits in (256, 1024):
+        rc, log, out = _run(sim, jp, sub_bits, tmp_path)
+        assert rc == 0, log
+        assert np.array_equal(np.fromfile(out, dtype=np.int16).reshape(-1, 64), coef), f"S={sub_bits}"

@@ -262,6 +262,20 @@ def test_rejects_other_sizes_garbage_and_damaged_streams(cvs, monkeypatch):
             assert e.status == 1
 
 
+@pytest.mark.parametrize("name,dc_len,ac_len", [("q95_420_200x150", 11, 10), ("q90_gray_123x77", 10, 12), ("q92_420_1280x720", 16, 16)])
+def test_uniform_long_codes(cvs, oracle, monkeypatch, name, dc_len, ac_len):
+    """Worst case for the decoder's look-up tables: every code dc_len / ac_len bits long (tests/util.transcode_huffman)."""
+    from util import transcode_huffman
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    jpg = z[name + "/jpg"].tobytes()
+    w, h = (int(v) for v in z[name + "/wh"])
+    info, coef = oracle.jpeg_info(jpg), oracle.jpeg_coefficients(jpg)
+    t = transcode_huffman(jpg, coef, info["hs"], info["vs"], info["ncomp"], dc_len, ac_len)
+    g = _decode(cvs, t, w, h)
+    assert hashlib.sha256(g.tobytes()).digest() == z[name + "/sha"].tobytes()
+
+
 def test_random_streams_against_opencv(cvs, oracle, monkeypatch):
     """Random pictures (smooth, noisy, saturated), sizes, qualities 3..100, samplings, optimised Huffman tables (unusual code
     length distributions: the second-level tables and the canonical slow path of the decoder's look-up) and restart
