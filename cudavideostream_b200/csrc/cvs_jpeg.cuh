@@ -5,16 +5,25 @@
 // A camera frame has no restart markers, so its Huffman stream is one sequential dependency chain (432 KB at 1080p).
 // It is decoded in parallel through the self-synchronisation of Huffman codes:
 //
-//   k_unstuff_count / k_unstuff_write   FF 00 -> FF: the entropy-coded segment becomes a plain bit string of T bits
-//   k_entropy (one cooperative launch)  the bit string is cut into subsequences of S bits, one thread each.
-//       sync     every thread decodes its subsequence from a guessed entry state (bit offset of the first token that
-//                starts in it, block-in-MCU phase, zig-zag position) and hands its exit state to its successor; whoever
-//                receives an entry state it has not used yet decodes again.  Thread 0's entry state is exact, a wrong
-//                guess falls into step with the true token sequence after a few dozen bits, so the states stop
-//                changing after a handful of rounds (any number is handled: a grid barrier per round, until no state
-//                changed).  Each run also leaves the blocks completed and the DC differences summed per component.
-//       scan     exclusive prefix sums of those give every subsequence its first block index and DC predictors
-//       write    each thread decodes once more from its now exact entry state and stores the coefficients
+//   k_entropy (one cooperative launch; phases separated by grid barriers)
+//       clear    the scratch that must start as zero; FF 00 -> FF: the entropy-coded segment becomes a plain bit string of
+//       unstuff  T bits (16 bytes per thread, kept bytes compacted by a two-level prefix sum)
+//       The bit string is cut into subsequences of S = 1,024 bits.  The decoder state at a boundary is (bit offset of the
+//       first token that starts behind it, block-in-MCU phase, zig-zag position).  A decoder started in a wrong state falls
+//       into step with the true token sequence -- but only once its PHASE is right too, because the luma blocks of an MCU
+//       share their tables, and the phase of a wrong guess performs a random walk (13-24 plain rounds on a camera frame).
+//       X Y W    so for every boundary and every phase h one thread decodes from "a block of phase h starts here" through
+//                three subsequences and notes its state at their ends: 2 * bpm candidate states per boundary
+//       maps     at which candidate of boundary i does the sequence through candidate c of boundary i-1 arrive?
+//       scan     the true sequence starts at candidate 0 of boundary 0; following it is a prefix scan of map compositions
+//       rounds   decode from the entry state, hand the exit state to the successor, whoever received a new state decodes
+//                again, until nothing changes: ONE round when the scan found every state (a camera frame), as many as
+//                it takes otherwise -- exact states travel one subsequence per round at least, so every stream decodes.
+//                A run also leaves the blocks completed, the DC differences summed and its state every 128 bits.
+//       sums     exclusive prefix sums give every subsequence its first block index and DC predictors
+//       write    one thread per 128 bits decodes once more from its exact state and stores the coefficients
+//   k_unstuff_count / k_unstuff_write / k_entropy_restart   scans WITH restart intervals: the markers are dropped with the
+//               stuffing, every interval starts in a known state and is decoded by one thread, no synchronisation
 //   k_idct      dequantisation + jidctint.c's accurate integer IDCT per 8x8 block -> Y / Cb / Cr planes
 //   k_colour    jdsample.c's h2v1 / h2v2 "fancy" upsampling (context rows replicated at the border) + jdcolor.c's
 //               fixed-point conversion, stored B, G, R
