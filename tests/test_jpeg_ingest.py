@@ -315,3 +315,15 @@ def test_random_streams_against_opencv(cvs, oracle, monkeypatch):
         g = _decode(cvs, enc.tobytes(), w, h)
         bad = np.flatnonzero(g != ref)
         assert bad.size == 0, f"case {case} ({w}x{h}, {params}): {bad.size} bytes differ, first at {bad[:5]}"
+
+
+def test_many_tickets_on_several_streams(cvs):
+    """scripts/jpeg_soak.py in small: 3 streams x 120 tickets through cvs_submit_jpeg with four tickets in flight each (the
+    tickets of a stream alternate between two decode streams with their own scratch): every ticket delivers the same
+    payload on every stream, and the payloads repeat with the two camera frames."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "jpeg_soak.py"), "3", "120"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=170, env=dict(os.environ, CVS_JPEG_DECODER="own"))
+    assert r.returncode == 0, r.stdout.decode()[-800:]
