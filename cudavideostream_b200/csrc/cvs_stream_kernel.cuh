@@ -215,10 +215,15 @@ __device__ __forceinline__ uint8_t *at_u8(uint8_t *base, uint32_t i)
 // instead of shuffles and popcounts.  CHECK = false when the warp's whole run fits the payload capacity.
 // This loop is the bulk of a dense frame's instructions.
 // nchunk: chunks the warp holds (lanes >= nchunk have an empty mask); a multiple of the batch size.
-template <bool CHECK>
+// STAGE_DIFF: the difference bytes are not stored to global memory one by one but compacted IN PLACE in the warp's part
+// of the ring stage (an entry's rank inside the warp is never larger than its byte position, and the chunks are
+// walked front to back, so a write never lands on a byte that is still to be read); the caller then flushes the
+// g_warp0-based run with whole words (flush_diff_shifted in cvs_stream_ws.cuh).  g_warp0 = global rank of the warp's
+// first entry.
+template <bool CHECK, bool STAGE_DIFF = false>
 __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint32_t coff0, uint32_t dvaddr0,
                                           int *xs_out, uint8_t *df_out, uint32_t g_lane, uint32_t cap32, uint32_t lane,
-                                          uint32_t scratch, uint32_t nchunk = 32)
+                                          uint32_t scratch, uint32_t nchunk = 32, uint32_t g_warp0 = 0)
 {
     {
         const uint32_t r1 = g_lane + (uint32_t)__popc(m[0]), r2 = r1 + (uint32_t)__popc(m[1]);
@@ -248,6 +253,7 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
         for (int i = 0; i < kBatch; i++)
 #pragma unroll
             for (int w = 0; w < kMaskWords; w++) v[i][w] = lds_u8(dvaddr0 + (S0 + i) * kChunkBytes + lane + 32 * w);
+        if (STAGE_DIFF) __syncwarp(); // every lane has read the batch's bytes before anybody overwrites them
 #pragma unroll
         for (int i = 0; i < kBatch; i++) {
             const uint32_t cb = coff0 + (S0 + i) * kChunkBytes + lane;
@@ -257,11 +263,19 @@ __device__ __forceinline__ void emit_coop(const uint32_t (&m)[kMaskWords], uint3
                 // both stores under one predicate (no branch around two instructions)
                 uint32_t on = sm[i][w] & lanebit;
                 if (CHECK && g >= cap32) on = 0;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
-                             "@p st.global.cs.u32 [%1], %2;\n\t"
-                             "@p st.global.cs.u8 [%3], %4;\n\t}" ::"r"(on), "l"(at_u32(xs_out, g)), "r"(cb + 32 * w),
-                             "l"(at_u8(df_out, g)), "r"(v[i][w])
-                             : "memory");
+                if (STAGE_DIFF) {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+                                 "@p st.global.cs.u32 [%1], %2;\n\t"
+                                 "@p st.shared.u8 [%3], %4;\n\t}" ::"r"(on), "l"(at_u32(xs_out, g)), "r"(cb + 32 * w),
+                                 "r"(dvaddr0 + (g - g_warp0)), "r"(v[i][w])
+                                 : "memory");
+                } else {
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0;\n\t"
+                                 "@p st.global.cs.u32 [%1], %2;\n\t"
+                                 "@p st.global.cs.u8 [%3], %4;\n\t}" ::"r"(on), "l"(at_u32(xs_out, g)), "r"(cb + 32 * w),
+                                 "l"(at_u8(df_out, g)), "r"(v[i][w])
+                                 : "memory");
+                }
             }
         }
     }
