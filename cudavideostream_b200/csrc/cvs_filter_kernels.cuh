@@ -104,20 +104,8 @@ __device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi)
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
     return r;
 }
-__device__ __forceinline__ float lo2(f32x2 v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)hi;
-    return lo;
-}
-__device__ __forceinline__ float hi2(f32x2 v)
-{
-    float lo, hi;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-    (void)lo;
-    return hi;
-}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
 __device__ __forceinline__ f32x2 fma2_bcast(float a, f32x2 b, f32x2 c) // {a, a} * b + c
 {
     asm("{ .reg .b64 ra;\n mov.b64 ra, {%1, %1};\n fma.rn.f32x2 %0, ra, %2, %0; }" : "+l"(c) : "f"(a), "l"(b));
