@@ -174,7 +174,7 @@ struct JpegDecoder {
     std::vector<uint8_t> header;   // ... and its bytes up to the scan (a camera repeats them: no table rebuild per frame)
     cvs::jpg::Tables tables_host;  // what d_tables holds
     bool tables_valid = false;
-    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr, *d_hw = nullptr;
+    uint32_t *d_entry = nullptr, *d_used = nullptr, *d_nblk = nullptr, *d_tile_blk = nullptr, *d_hx = nullptr, *d_hy = nullptr, *d_hw = nullptr, *d_hym = nullptr, *d_hwm = nullptr;
     uint8_t *d_hmap = nullptr;
     uint32_t *d_mid_state = nullptr, *d_mid_nblk = nullptr;
     int32_t *d_mid_dc = nullptr;
@@ -1003,23 +1003,25 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
         cudaFree(jd.d_arena);
         jd.d_arena = nullptr;
         jd.raw_cap = jd.block_cap = jd.sub_cap = 0;
-        const size_t nsub_cap = (raw_cap * 8 + jd.sub_bits - 1) / jd.sub_bits + 1, ntile_cap = nsub_cap / J::kEntropyThreads + 2;
+        const size_t nsub_cap = (raw_cap * 8 + jd.sub_bits - 1) / jd.sub_bits + 1;
+        const size_t nhalf_cap = 2 * nsub_cap, ntile_cap = nhalf_cap / J::kEntropyThreads + 2; // the rounds may work on half subsequences
         size_t off = 0;
         auto carve = [&](size_t bytes) {
             const size_t o = off;
             off += round_up(bytes, 256);
             return o;
         };
-        const size_t o_changed = carve(J::kRoundCounters * sizeof(unsigned int)), o_entry = carve((nsub_cap + 2) * sizeof(uint32_t)),
+        const size_t o_changed = carve(J::kRoundCounters * sizeof(unsigned int)), o_entry = carve((nhalf_cap + 2) * sizeof(uint32_t)),
                      o_unst = carve(raw_cap), o_coef = carve(block_cap * 64 * sizeof(int16_t));
         jd.zero_bytes_fixed = o_coef; // + nblocks * 128 of the coefficients
         const size_t o_raw = carve(raw_cap), o_kept = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),
                      o_marks = carve((raw_cap / (J::kUnstuffThreads * J::kUnstuffBytes) + 1) * sizeof(uint32_t)),
-                     o_seg = carve((block_cap + 2) * sizeof(uint32_t)), o_total = carve(2 * sizeof(uint32_t)), o_tables = carve(sizeof(J::Tables)), o_used = carve(nsub_cap * sizeof(uint32_t)),
-                     o_nblk = carve(nsub_cap * sizeof(uint32_t)), o_dcs = carve(3 * nsub_cap * sizeof(int32_t)),
+                     o_seg = carve((block_cap + 2) * sizeof(uint32_t)), o_total = carve(2 * sizeof(uint32_t)), o_tables = carve(sizeof(J::Tables)), o_used = carve(nhalf_cap * sizeof(uint32_t)),
+                     o_nblk = carve(nhalf_cap * sizeof(uint32_t)), o_dcs = carve(3 * nhalf_cap * sizeof(int32_t)),
                      o_tile_blk = carve(ntile_cap * sizeof(uint32_t)), o_tile_dc = carve(3 * ntile_cap * sizeof(int32_t)),
                      o_hx = carve(6 * nsub_cap * sizeof(uint32_t)), o_hy = carve(6 * nsub_cap * sizeof(uint32_t)),
-                     o_hw = carve(6 * nsub_cap * sizeof(uint32_t)),
+                     o_hw = carve(6 * nsub_cap * sizeof(uint32_t)), o_hym = carve(6 * nsub_cap * sizeof(uint32_t)),
+                     o_hwm = carve(6 * nsub_cap * sizeof(uint32_t)),
                      o_hmap = carve(16 * nsub_cap), o_mid_state = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
                      o_mid_nblk = carve(J::kMaxSplit * nsub_cap * sizeof(uint32_t)),
                      o_mid_dc = carve(3 * J::kMaxSplit * nsub_cap * sizeof(int32_t)), o_planes = carve(block_cap * 64 + 256);
@@ -1045,6 +1047,8 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
         jd.d_hx = reinterpret_cast<uint32_t *>(a + o_hx);
         jd.d_hy = reinterpret_cast<uint32_t *>(a + o_hy);
         jd.d_hw = reinterpret_cast<uint32_t *>(a + o_hw);
+        jd.d_hym = reinterpret_cast<uint32_t *>(a + o_hym);
+        jd.d_hwm = reinterpret_cast<uint32_t *>(a + o_hwm);
         jd.d_hmap = a + o_hmap;
         jd.d_mid_state = reinterpret_cast<uint32_t *>(a + o_mid_state);
         jd.d_mid_nblk = reinterpret_cast<uint32_t *>(a + o_mid_nblk);
@@ -1126,6 +1130,8 @@ static cvs_status jpeg_decode_own(cvs_handle h, JpegDecoder &jd, const uint8_t *
     ep.hx = jd.d_hx;
     ep.hy = jd.d_hy;
     ep.hw = jd.d_hw;
+    ep.hym = jd.d_hym;
+    ep.hwm = jd.d_hwm;
     ep.hmap = jd.d_hmap;
     ep.hypotheses = jd.hypotheses ? 1u : 0u;
     ep.changed = jd.d_changed;

@@ -17,8 +17,8 @@
 //       maps     at which candidate of boundary i does the sequence through candidate c of boundary i-1 arrive?
 //       scan     the true sequence starts at candidate 0 of boundary 0; following it is a prefix scan of map compositions
 //       rounds   decode from the entry state, hand the exit state to the successor, whoever received a new state decodes
-//                again, until nothing changes: ONE round when the scan found every state (a camera frame), as many as
-//                it takes otherwise -- exact states travel one subsequence per round at least, so every stream decodes.
+//                again, until nothing changes: ONE round when the scan found every state (a camera frame; on half
+//                subsequences then: the Y / W runs also note their state in the middle), as many as it takes otherwise -- exact states travel one subsequence per round at least, so every stream decodes.
 //                A run also leaves the blocks completed, the DC differences summed and its state every 128 bits.
 //       sums     exclusive prefix sums give every subsequence its first block index and DC predictors
 //       write    one thread per 128 bits decodes once more from its exact state and stores the coefficients
@@ -133,6 +133,7 @@ constexpr uint32_t kNoCandidate = 15u;
 // what one run over a subsequence leaves behind
 struct RunResult {
     uint32_t exit_state;
+    uint32_t half_state;        // HALF runs: state of the first token that starts in the second half (kStateUnset: none)
     uint32_t nblocks;           // blocks completed by tokens that start in this subsequence
     int32_t dc0, dc1, dc2;      // DC differences decoded in this subsequence, per component
 };
@@ -235,7 +236,7 @@ struct MidRecords {
 // The token step is one code path for DC and AC tokens, written with selects: the lanes of a warp sit in different places
 // of different blocks, divergent paths would put their latencies in series, and the chain p -> window -> table -> p is
 // what the whole decode waits for.
-template <bool WRITE, bool RECORD = false>
+template <bool WRITE, bool RECORD = false, bool HALF = false>
 CVS_HD RunResult run_range(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t begin,
                            uint32_t end_nominal, uint32_t i, uint32_t entry, const uint8_t *natural, int16_t *coef,
                            uint32_t first_block, int32_t pred0, int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
@@ -247,10 +248,16 @@ CVS_HD RunResult run_range(const TableRef &tb, const Geometry &g, const uint32_t
     uint32_t blk = first_block, nblocks = 0;
     const uint32_t nluma = (uint32_t)(g.bpm - (g.ncomp == 3 ? 2 : 0)), bpm = (uint32_t)g.bpm;
     uint32_t next_inner = 0, inner = 1;
+    // (the fields of *mid in locals: the record stores below could alias them, and they would be re-read per token)
+    uint32_t *const rec_state = RECORD ? mid->state : nullptr, *const rec_nblk = RECORD ? mid->nblk : nullptr;
+    int32_t *const rec_dc = RECORD ? mid->dc : nullptr;
+    const uint32_t rec_G = RECORD ? mid->G : 0u, rec_nsplit = RECORD ? mid->nsplit : 0u, rec_stride = RECORD ? mid->stride : 0u;
     if (RECORD) {
-        next_inner = begin + mid->G;
-        for (uint32_t j = 1; j < mid->nsplit; j++) mid->state[i * mid->nsplit + j] = kStateUnset;
+        next_inner = begin + rec_G;
+        for (uint32_t j = 1; j < rec_nsplit; j++) rec_state[i * rec_nsplit + j] = kStateUnset;
     }
+    const uint32_t half_at = begin + ((end_nominal - begin) >> 1);
+    uint32_t half = kStateUnset;
     if (begin < total_bits && p < end) {
         BitWindow bw;
         bw.init(words, p);
@@ -283,20 +290,25 @@ CVS_HD RunResult run_range(const TableRef &tb, const Geometry &g, const uint32_t
             nblocks += block_end ? 1u : 0u;
             if (RECORD) {
                 if (p >= next_inner && p < end) { // the first token behind an inner boundary starts at p
-                    const uint32_t idx = i * mid->nsplit + inner;
-                    mid->state[idx] = pack_state(p - next_inner, ph, k);
-                    mid->nblk[idx] = nblocks;
-                    mid->dc[idx] = dc0 - pred0;
-                    mid->dc[mid->stride + idx] = dc1 - pred1;
-                    mid->dc[2 * mid->stride + idx] = dc2 - pred2;
-                    next_inner += mid->G;
+                    const uint32_t idx = i * rec_nsplit + inner;
+                    rec_state[idx] = pack_state(p - next_inner, ph, k);
+                    rec_nblk[idx] = nblocks;
+                    rec_dc[idx] = dc0 - pred0;
+                    rec_dc[rec_stride + idx] = dc1 - pred1;
+                    rec_dc[2 * rec_stride + idx] = dc2 - pred2;
+                    next_inner += rec_G;
                     inner++;
                 }
+            }
+            if (HALF) { // the first token of the second half starts at p
+                const bool hit = half == kStateUnset && p >= half_at && p < end;
+                half = hit ? pack_state(p - half_at, ph, k) : half;
             }
         } while (p < end);
     }
     const uint32_t over = p > end_nominal ? p - end_nominal : 0u; // < 32: a token is at most 31 bits long
     r.exit_state = pack_state(over & 31u, ph, k);
+    r.half_state = half;
     r.nblocks = nblocks;
     r.dc0 = WRITE ? dc0 : dc0 - pred0; // sums of the differences when counting
     r.dc1 = WRITE ? dc1 : dc1 - pred1;
@@ -304,12 +316,12 @@ CVS_HD RunResult run_range(const TableRef &tb, const Geometry &g, const uint32_t
     return r;
 }
 
-template <bool WRITE, bool RECORD = false>
+template <bool WRITE, bool RECORD = false, bool HALF = false>
 CVS_HD RunResult run_subsequence(const TableRef &tb, const Geometry &g, const uint32_t *words, uint32_t total_bits, uint32_t i,
                                  uint32_t entry, const uint8_t *natural, int16_t *coef, uint32_t first_block, int32_t pred0,
                                  int32_t pred1, int32_t pred2, const MidRecords *mid = nullptr)
 {
-    return run_range<WRITE, RECORD>(tb, g, words, total_bits, i * g.sub_bits, i * g.sub_bits + g.sub_bits, i, entry, natural, coef,
+    return run_range<WRITE, RECORD, HALF>(tb, g, words, total_bits, i * g.sub_bits, i * g.sub_bits + g.sub_bits, i, entry, natural, coef,
                                     first_block, pred0, pred1, pred2, mid);
 }
 
@@ -542,7 +554,7 @@ struct EntropyParams {
     Geometry g;
     const uint32_t *words;    // unstuffed string
     const uint32_t *total_bits;
-    uint32_t *entry;          // [nsub_max + 1] entry state of each subsequence (written by its predecessor)
+    uint32_t *entry;          // [2 * nsub_max + 2] entry state of each (half) subsequence (written by its predecessor)
     uint32_t *used;           // [nsub_max] entry state of the last run
     uint32_t *nblk;           // [nsub_max] blocks completed, then (after the scan) first block index
     int32_t *dcs;             // [3][nsub_max] DC sums, then predictors at entry
@@ -550,6 +562,7 @@ struct EntropyParams {
     int32_t *tile_dc;         // [3][ntiles]
     MidRecords mid;           // inner-boundary records of the counting runs (write pass granularity)
     uint32_t *hx, *hy, *hw;   // [nsub_max * bpm] exit states of the phase hypotheses: fresh / followed one / two subsequences further
+    uint32_t *hym, *hwm;      // [nsub_max * bpm] state of the Y / W runs in the middle of their subsequence (hym[0]: the exact run of subsequence 0)
     uint8_t *hmap;            // [nsub_max][16] successor of candidate c of boundary i-1 among the candidates of boundary i
     uint32_t hypotheses;      // 0: plain rounds from the guess "a block starts here" (A/B measurements)
     unsigned int *changed;    // [kRoundCounters] states changed in a round, three counters in rotation
@@ -598,7 +611,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         for (uint32_t j = gtid; j < g.nblocks * 8u; j += gthreads) cz[j] = z; // 128 bytes per block
         uint4 *uz = reinterpret_cast<uint4 *>(p.unst);
         for (uint32_t j = gtid; j < p.unst_bytes / 16u; j += gthreads) uz[j] = z;
-        for (uint32_t j = gtid; j < g.nsub_max + 2u; j += gthreads) p.entry[j] = 0u; // first guess: a block of phase 0 starts here
+        for (uint32_t j = gtid; j < 2u * g.nsub_max + 2u; j += gthreads) p.entry[j] = 0u; // first guess: a block of phase 0 starts here
         if (gtid < (uint32_t)kRoundCounters) p.changed[gtid] = 0u;
         const uint32_t nvb = (p.raw_len + kUnstuffThreads * kUnstuffBytes - 1) / (kUnstuffThreads * kUnstuffBytes);
         for (uint32_t vb = blockIdx.x; vb < nvb; vb += gridDim.x) unstuff_count_block(vb, p.raw, p.raw_len, p.block_kept, p.block_marks, wsum);
@@ -616,6 +629,10 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     const uint32_t nsub = (T + g.sub_bits - 1) / g.sub_bits; // <= nsub_max
     const uint32_t ntiles = (nsub + kEntropyThreads - 1) / kEntropyThreads;
 
+    // the rounds, the prefix sums and the write pass work on HALF subsequences when the hypotheses deliver the states in
+    // the middle of the subsequences too (half the length of the confirming round)
+    const bool half = p.hypotheses && g.sub_bits % 256u == 0 && p.mid.nsplit % 2u == 0;
+    const uint32_t hstep = half ? 2u : 1u;
     // ---- phase hypotheses (see the header): seed entry[] with the states the true token sequence passes through
     if (p.hypotheses) {
         const uint32_t B = (uint32_t)g.bpm, nh = nsub * B, gstride = gridDim.x * kEntropyThreads;
@@ -626,14 +643,27 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         // 600 on the camera frame) instead of three times for the slowest subsequence of the frame (3 x 286).
         for (uint32_t idx = first; idx < nh; idx += gstride) {
             const uint32_t i = idx / B, h = idx - i * B;
-            const uint32_t x = run_subsequence<false>(tbr, g, p.words, T, i, pack_state(0, h, 0), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            uint32_t x;
+            if (idx == 0) { // the exact start: this is the decode of subsequence 0, its middle state is wanted below
+                const RunResult r0 = run_subsequence<false, false, true>(tbr, g, p.words, T, 0, pack_state(0, 0, 0), s_nat, nullptr, 0, 0, 0, 0);
+                x = r0.exit_state;
+                p.hym[0] = r0.half_state;
+            } else {
+                x = run_subsequence<false>(tbr, g, p.words, T, i, pack_state(0, h, 0), s_nat, nullptr, 0, 0, 0, 0).exit_state;
+            }
             p.hx[idx] = x;
             if (i == 0) p.hy[idx] = kStateUnset;
             if (i + 1 < nsub) {
-                const uint32_t y = run_subsequence<false>(tbr, g, p.words, T, i + 1, x, s_nat, nullptr, 0, 0, 0, 0).exit_state;
-                p.hy[idx + B] = y;
-                if (i + 2 < nsub)
-                    p.hw[idx + 2 * B] = run_subsequence<false>(tbr, g, p.words, T, i + 2, y, s_nat, nullptr, 0, 0, 0, 0).exit_state;
+                // (a Y / W run that starts from the TRUE state of its boundary is the decode of its subsequence: its state
+                //  in the middle lets the rounds below work on half subsequences)
+                const RunResult ry = run_subsequence<false, false, true>(tbr, g, p.words, T, i + 1, x, s_nat, nullptr, 0, 0, 0, 0);
+                p.hy[idx + B] = ry.exit_state;
+                p.hym[idx + B] = ry.half_state;
+                if (i + 2 < nsub) {
+                    const RunResult rw = run_subsequence<false, false, true>(tbr, g, p.words, T, i + 2, ry.exit_state, s_nat, nullptr, 0, 0, 0, 0);
+                    p.hw[idx + 2 * B] = rw.exit_state;
+                    p.hwm[idx + 2 * B] = rw.half_state;
+                }
             }
         }
         grid.sync();
@@ -697,13 +727,24 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
                 __syncthreads();
             }
             uint32_t t = tid ? (uint32_t)(s_f[tid - 1]) & 15u : 0u; // candidate the true sequence is at boundary lo - 1
-            if (tid == 0) p.entry[1] = __ldcg(p.hx); // boundary 0: the exact run
+            // entry[] is filled at the granularity the rounds use: 2 * i = start of subsequence i, 2 * i + 1 = its middle
+            // (hstep = 2), or just the subsequence starts (hstep = 1)
+            if (tid == 0) {
+                p.entry[hstep] = __ldcg(p.hx); // boundary 0: the exact run
+                if (half) p.entry[1] = __ldcg(p.hym) == kStateUnset ? 0u : __ldcg(p.hym);
+            }
             for (uint32_t i = lo; i < hi; i++) {
+                if (half) { // subsequence i was decoded from candidate t of boundary i - 1: by its Y run (t < B) or its W run
+                    uint32_t hs = kStateUnset;
+                    if (t < B) hs = __ldcg(p.hym + i * B + t);
+                    else if (t < 2 * B) hs = __ldcg(p.hwm + i * B + t - B);
+                    p.entry[2 * i + 1] = hs == kStateUnset ? 0u : hs;
+                }
                 if (t < 12u) t = p.hmap[(size_t)i * 16 + t];
                 uint32_t st = __ldcg(p.hx + i * B); // no candidate known: any state, the rounds below repair it
                 if (t < B) st = __ldcg(p.hx + i * B + t);
                 else if (t < 2 * B) st = __ldcg(p.hy + i * B + t - B);
-                p.entry[i + 1] = st;
+                p.entry[hstep * (i + 1)] = st;
             }
         }
         __threadfence();
@@ -714,33 +755,43 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         }
     }
 
+    Geometry gr = g;
+    MidRecords midr = p.mid;
+    uint32_t nsubr = nsub, ntilesr = ntiles;
+    if (half) {
+        gr.sub_bits = g.sub_bits / 2u;
+        gr.nsub_max = 2u * g.nsub_max;
+        midr.nsplit = p.mid.nsplit / 2u; // the inner boundaries stay where they were (every G bits)
+        nsubr = (T + gr.sub_bits - 1) / gr.sub_bits;
+        ntilesr = (nsubr + kEntropyThreads - 1) / kEntropyThreads;
+    }
     // ---- rounds: decode from the entry state, hand the exit state on, until no state changes (one round when the
     //      seeds above are all true; any number otherwise).  (Measured and not adopted: letting the Y / W runs keep their
     //      counts and inner-boundary records -- the run that started from the true state of its boundary IS the decode,
     //      so this round could go -- makes those phases 183 us instead of 123 us with six times the records to store;
     //      317 us per frame either way.)
     bool converged = false;
-    // Exact states travel at least one subsequence per round, so nsub rounds always suffice (a stream whose codes do not
+    // Exact states travel at least one subsequence per round, so nsubr rounds always suffice (a stream whose codes do not
     // self-synchronise at all -- every code equally long -- needs them all; a camera frame needs one).  The counter of a
     // round is one of three in rotation: the one of round r + 1 is cleared during round r, when every thread has long
     // read it for round r - 2.
-    for (uint32_t round = 0; round <= nsub; round++) {
+    for (uint32_t round = 0; round <= nsubr; round++) {
         unsigned int *const counter = p.changed + round % 3u;
         if (blockIdx.x == 0 && tid == 0) p.changed[(round + 1u) % 3u] = 0u;
-        for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (uint32_t tile = blockIdx.x; tile < ntilesr; tile += gridDim.x) {
             const uint32_t i = tile * kEntropyThreads + tid;
-            if (i >= nsub) continue;
+            if (i >= nsubr) continue;
             const uint32_t e = i == 0 ? pack_state(0, 0, 0) : __ldcg(p.entry + i);
             if (round && e == p.used[i]) continue;
-            const RunResult r = run_subsequence<false, true>(tbr, g, p.words, T, i, e, s_nat, nullptr, 0, 0, 0, 0, &p.mid);
+            const RunResult r = run_subsequence<false, true>(tbr, gr, p.words, T, i, e, s_nat, nullptr, 0, 0, 0, 0, &midr);
             p.used[i] = e;
             p.nblk[i] = r.nblocks;
             p.dcs[i] = r.dc0;
-            p.dcs[g.nsub_max + i] = r.dc1;
-            p.dcs[2 * g.nsub_max + i] = r.dc2;
+            p.dcs[gr.nsub_max + i] = r.dc1;
+            p.dcs[2 * gr.nsub_max + i] = r.dc2;
             if (__ldcg(p.entry + i + 1) != r.exit_state) {
                 __stcg(p.entry + i + 1, r.exit_state);
-                if (i + 1 < nsub) atomicAdd(counter, 1u);
+                if (i + 1 < nsubr) atomicAdd(counter, 1u);
             }
         }
         const unsigned long long t_run = trace ? jpg_now_ns() : 0ull;
@@ -762,14 +813,14 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     }
 
     // ---- scan: per-tile totals, then every tile sums the totals in front of it
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < ntilesr; tile += gridDim.x) {
         const uint32_t i = tile * kEntropyThreads + tid;
         uint32_t v[4] = {0, 0, 0, 0};
-        if (i < nsub) {
+        if (i < nsubr) {
             v[0] = p.nblk[i];
             v[1] = (uint32_t)p.dcs[i];
-            v[2] = (uint32_t)p.dcs[g.nsub_max + i];
-            v[3] = (uint32_t)p.dcs[2 * g.nsub_max + i];
+            v[2] = (uint32_t)p.dcs[gr.nsub_max + i];
+            v[3] = (uint32_t)p.dcs[2 * gr.nsub_max + i];
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -781,20 +832,20 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
             uint32_t t = 0;
             for (int w = 0; w < kEntropyThreads / 32; w++) t += s_scan[tid][w];
             if (tid == 0) p.tile_blk[tile] = t;
-            else p.tile_dc[(tid - 1) * ntiles + tile] = (int32_t)t;
+            else p.tile_dc[(tid - 1) * ntilesr + tile] = (int32_t)t;
         }
         __syncthreads();
     }
     grid.sync();
     uint32_t total_blocks_seen = 0;
-    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < ntilesr; tile += gridDim.x) {
         // base of this tile
         uint32_t part[4] = {0, 0, 0, 0};
         for (uint32_t j = tid; j < tile; j += kEntropyThreads) {
             part[0] += __ldcg(p.tile_blk + j);
             part[1] += (uint32_t)__ldcg(p.tile_dc + j);
-            part[2] += (uint32_t)__ldcg(p.tile_dc + ntiles + j);
-            part[3] += (uint32_t)__ldcg(p.tile_dc + 2 * ntiles + j);
+            part[2] += (uint32_t)__ldcg(p.tile_dc + ntilesr + j);
+            part[3] += (uint32_t)__ldcg(p.tile_dc + 2 * ntilesr + j);
         }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -813,11 +864,11 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         // exclusive scan inside the tile
         const uint32_t i = tile * kEntropyThreads + tid;
         uint32_t v[4] = {0, 0, 0, 0};
-        if (i < nsub) {
+        if (i < nsubr) {
             v[0] = p.nblk[i];
             v[1] = (uint32_t)p.dcs[i];
-            v[2] = (uint32_t)p.dcs[g.nsub_max + i];
-            v[3] = (uint32_t)p.dcs[2 * g.nsub_max + i];
+            v[2] = (uint32_t)p.dcs[gr.nsub_max + i];
+            v[3] = (uint32_t)p.dcs[2 * gr.nsub_max + i];
         }
         uint32_t incl[4];
 #pragma unroll
@@ -839,12 +890,12 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
         }
         __syncthreads();
         // first block index and DC predictors of the subsequence (over the counts, which are not needed any more)
-        if (i < nsub) {
-            if (i == nsub - 1) total_blocks_seen = base[0] + v[0];
+        if (i < nsubr) {
+            if (i == nsubr - 1) total_blocks_seen = base[0] + v[0];
             p.nblk[i] = base[0];
             p.dcs[i] = (int32_t)base[1];
-            p.dcs[g.nsub_max + i] = (int32_t)base[2];
-            p.dcs[2 * g.nsub_max + i] = (int32_t)base[3];
+            p.dcs[gr.nsub_max + i] = (int32_t)base[2];
+            p.dcs[2 * gr.nsub_max + i] = (int32_t)base[3];
         }
     }
     grid.sync();
@@ -854,20 +905,20 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     }
     // ---- write pass: one thread per G bits, from the states the counting runs left at the inner boundaries
     {
-        Geometry gw = g;
-        gw.sub_bits = p.mid.G;
-        const uint32_t nsplit = p.mid.nsplit, nparts = nsub * nsplit;
+        Geometry gw = gr;
+        gw.sub_bits = midr.G;
+        const uint32_t nsplit = midr.nsplit, nparts = nsubr * nsplit;
         for (uint32_t j = blockIdx.x * kEntropyThreads + tid; j < nparts; j += gridDim.x * kEntropyThreads) {
             const uint32_t i = j / nsplit, part = j - i * nsplit;
             uint32_t e = __ldcg(p.used + i), blk0 = __ldcg(p.nblk + i);
-            int32_t d0 = __ldcg(p.dcs + i), d1 = __ldcg(p.dcs + g.nsub_max + i), d2 = __ldcg(p.dcs + 2 * g.nsub_max + i);
+            int32_t d0 = __ldcg(p.dcs + i), d1 = __ldcg(p.dcs + gr.nsub_max + i), d2 = __ldcg(p.dcs + 2 * gr.nsub_max + i);
             if (part) {
-                e = __ldcg(p.mid.state + j);
+                e = __ldcg(midr.state + j);
                 if (e == kStateUnset) continue;
-                blk0 += __ldcg(p.mid.nblk + j);
-                d0 += __ldcg(p.mid.dc + j);
-                d1 += __ldcg(p.mid.dc + p.mid.stride + j);
-                d2 += __ldcg(p.mid.dc + 2 * p.mid.stride + j);
+                blk0 += __ldcg(midr.nblk + j);
+                d0 += __ldcg(midr.dc + j);
+                d1 += __ldcg(midr.dc + midr.stride + j);
+                d2 += __ldcg(midr.dc + 2 * midr.stride + j);
             }
             run_subsequence<true>(tbr, gw, p.words, T, j, e, s_nat, p.coef, blk0, d0, d1, d2);
         }
@@ -875,7 +926,7 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     if (trace) printf("write pass (block 0): %llu ns\n", jpg_now_ns() - t_prev);
     // the string must hold exactly the image's blocks (padding bits after the last block decode to no complete block
     // in a well-formed stream; more or fewer blocks means a damaged frame)
-    if (total_blocks_seen && total_blocks_seen < g.nblocks) atomicOr(p.status, kJpegBlockCount);
+    if (total_blocks_seen && total_blocks_seen < gr.nblocks) atomicOr(p.status, kJpegBlockCount);
 }
 
 // ---- IDCT: jidctint.c jpeg_idct_islow, one thread per 8x8 block ---------------------------------------------------------

@@ -44,21 +44,32 @@ int main(int argc, char **argv)
     const Geometry g = P.g;
     const TableRef tbr = table_ref(&P.t);
     const uint32_t nsub = (T + S - 1) / S;
-    std::vector<uint32_t> entry(nsub + 2, 0), used(nsub, 0), nblk(nsub, 0);
-    std::vector<int32_t> dcs(3 * (size_t)nsub, 0);
     const bool hypotheses = argc < 5 || atoi(argv[4]) != 0;
+    // the rounds, the prefix sums and the write pass work on HALF subsequences when the hypotheses deliver the states in the
+    // middle of the subsequences too (as k_entropy does)
+    MidRecords mid;
+    mid.nsplit = S % 256 == 0 ? 8u : (S % 128 == 0 ? 4u : 1u);
+    mid.G = S / mid.nsplit;
+    const bool half = hypotheses && S % 256 == 0 && mid.nsplit % 2 == 0;
+    const uint32_t hstep = half ? 2u : 1u;
+    std::vector<uint32_t> entry(2 * (size_t)nsub + 2, 0);
     if (hypotheses) {
         // k_entropy's hypothesis phases: X (a block of phase h starts at the boundary), Y (X of the subsequence in front
         // followed through this one), W (Y followed once more) and the maps "candidate of boundary i-1 -> candidate of
         // boundary i"; candidate 0 of boundary 0 is followed through the maps and its states seed entry[]
         const uint32_t B = (uint32_t)g.bpm;
-        std::vector<uint32_t> hx((size_t)nsub * B), hy((size_t)nsub * B, kStateUnset);
+        std::vector<uint32_t> hx((size_t)nsub * B), hy((size_t)nsub * B, kStateUnset), hym((size_t)nsub * B, kStateUnset),
+            hwm((size_t)nsub * B, kStateUnset);
         std::vector<uint8_t> hmap((size_t)nsub * 16, (uint8_t)kNoCandidate);
-        auto run = [&](uint32_t i, uint32_t e) { return run_subsequence<false>(tbr, g, words, T, i, e, kZigzagNatural, nullptr, 0, 0, 0, 0).exit_state; };
+        auto run = [&](uint32_t i, uint32_t e, uint32_t *hs) {
+            const RunResult r = run_subsequence<false, false, true>(tbr, g, words, T, i, e, kZigzagNatural, nullptr, 0, 0, 0, 0);
+            if (hs) *hs = r.half_state;
+            return r.exit_state;
+        };
         for (uint32_t i = 0; i < nsub; i++)
-            for (uint32_t h = 0; h < B; h++) hx[(size_t)i * B + h] = run(i, pack_state(0, h, 0));
+            for (uint32_t h = 0; h < B; h++) hx[(size_t)i * B + h] = run(i, pack_state(0, h, 0), (i == 0 && h == 0) ? &hym[0] : nullptr);
         for (uint32_t i = 1; i < nsub; i++)
-            for (uint32_t h = 0; h < B; h++) hy[(size_t)i * B + h] = run(i, hx[(size_t)(i - 1) * B + h]);
+            for (uint32_t h = 0; h < B; h++) hy[(size_t)i * B + h] = run(i, hx[(size_t)(i - 1) * B + h], &hym[(size_t)i * B + h]);
         for (uint32_t i = 1; i < nsub; i++)
             for (uint32_t h = 0; h < B; h++) {
                 uint32_t m0 = B + h, m1 = kNoCandidate;
@@ -68,7 +79,7 @@ int main(int argc, char **argv)
                         break;
                     }
                 if (i >= 2) {
-                    const uint32_t w = run(i, hy[(size_t)(i - 1) * B + h]);
+                    const uint32_t w = run(i, hy[(size_t)(i - 1) * B + h], &hwm[(size_t)i * B + h]);
                     for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
                         if (hx[(size_t)i * B + h2] == w) m1 = h2;
                     for (uint32_t h2 = 0; h2 < B && m1 == kNoCandidate; h2++)
@@ -78,22 +89,35 @@ int main(int argc, char **argv)
                 hmap[(size_t)i * 16 + B + h] = (uint8_t)m1;
             }
         uint32_t t = 0, lost = 0;
-        entry[1] = hx[0];
+        entry[hstep] = hx[0];
+        if (half) entry[1] = hym[0] == kStateUnset ? 0u : hym[0];
         for (uint32_t i = 1; i < nsub; i++) {
+            if (half) {
+                uint32_t hs = kStateUnset;
+                if (t < B) hs = hym[(size_t)i * B + t];
+                else if (t < 2 * B) hs = hwm[(size_t)i * B + t - B];
+                entry[2 * i + 1] = hs == kStateUnset ? 0u : hs;
+            }
             if (t < 12u) t = hmap[(size_t)i * 16 + t];
             uint32_t st = hx[(size_t)i * B];
             if (t < B) st = hx[(size_t)i * B + t];
             else if (t < 2 * B) st = hy[(size_t)i * B + t - B];
             else lost++;
-            entry[i + 1] = st;
+            entry[hstep * (i + 1)] = st;
         }
         printf("hypotheses: %u of %u boundaries without a candidate\n", lost, nsub);
     }
+    Geometry gr = g;
+    uint32_t nsubr = nsub;
+    if (half) {
+        gr.sub_bits = S / 2;
+        mid.nsplit /= 2;
+        nsubr = (T + gr.sub_bits - 1) / gr.sub_bits;
+    }
+    std::vector<uint32_t> used(nsubr, 0), nblk(nsubr, 0);
+    std::vector<int32_t> dcs(3 * (size_t)nsubr, 0);
     // inner-boundary records of the counting runs: the write pass runs with one thread per G bits (as k_entropy does)
-    MidRecords mid;
-    mid.nsplit = S % 256 == 0 ? 8u : (S % 128 == 0 ? 4u : 1u);
-    mid.G = S / mid.nsplit;
-    mid.stride = mid.nsplit * nsub;
+    mid.stride = mid.nsplit * nsubr;
     std::vector<uint32_t> mid_state((size_t)mid.stride, kStateUnset), mid_nblk((size_t)mid.stride, 0);
     std::vector<int32_t> mid_dc(3 * (size_t)mid.stride, 0);
     mid.state = mid_state.data();
@@ -103,31 +127,31 @@ int main(int argc, char **argv)
     for (uint32_t round = 0;; round++) {
         std::vector<uint32_t> entry_in = entry; // all threads of a round see the states of the previous round
         uint32_t changed = 0, runs = 0;
-        for (uint32_t i = 0; i < nsub; i++) {
+        for (uint32_t i = 0; i < nsubr; i++) {
             const uint32_t e = i == 0 ? pack_state(0, 0, 0) : entry_in[i];
             if (round && e == used[i]) continue;
             runs++;
-            const RunResult r = run_subsequence<false, true>(tbr, g, words, T, i, e, kZigzagNatural, nullptr, 0, 0, 0, 0, &mid);
+            const RunResult r = run_subsequence<false, true>(tbr, gr, words, T, i, e, kZigzagNatural, nullptr, 0, 0, 0, 0, &mid);
             used[i] = e;
             nblk[i] = r.nblocks;
-            dcs[i] = r.dc0; dcs[(size_t)nsub + i] = r.dc1; dcs[2 * (size_t)nsub + i] = r.dc2;
+            dcs[i] = r.dc0; dcs[(size_t)nsubr + i] = r.dc1; dcs[2 * (size_t)nsubr + i] = r.dc2;
             if (entry[i + 1] != r.exit_state) {
                 entry[i + 1] = r.exit_state;
-                if (i + 1 < nsub) changed++;
+                if (i + 1 < nsubr) changed++;
             }
         }
         printf("round %u: %u runs, %u exit states changed\n", round, runs, changed);
         rounds = (int)round + 1;
         if (!changed) break;
-        if (round > 100000) return 5;
+        if (round > 1000000) return 5;
     }
     std::vector<int16_t> coef((size_t)g.nblocks * 64, 0);
     uint32_t base = 0;
     int32_t pred[3] = {0, 0, 0};
     uint32_t total = 0;
-    Geometry gw = g;
+    Geometry gw = gr;
     gw.sub_bits = mid.G;
-    for (uint32_t i = 0; i < nsub; i++) {
+    for (uint32_t i = 0; i < nsubr; i++) {
         uint32_t seen = 0;
         for (uint32_t part = 0; part < mid.nsplit; part++) {
             const uint32_t j = i * mid.nsplit + part;
@@ -144,7 +168,7 @@ int main(int argc, char **argv)
         }
         if (seen != nblk[i]) return 6;
         base += nblk[i];
-        for (int c = 0; c < 3; c++) pred[c] += dcs[(size_t)c * nsub + i];
+        for (int c = 0; c < 3; c++) pred[c] += dcs[(size_t)c * nsubr + i];
         total = base;
     }
     printf("rounds %d subsequences %u bits %u blocks %u expected %u\n", rounds, nsub, T, total, g.nblocks);
