@@ -630,7 +630,10 @@ __global__ void __launch_bounds__(kEntropyThreads) k_entropy(const EntropyParams
     const uint32_t ntiles = (nsub + kEntropyThreads - 1) / kEntropyThreads;
 
     // the rounds, the prefix sums and the write pass work on HALF subsequences when the hypotheses deliver the states in
-    // the middle of the subsequences too (half the length of the confirming round)
+    // the middle of the subsequences too (half the length of the confirming round).  (The state in the middle costs a
+    // compare and a select per token.  Measured and not adopted: the state at EVERY 128-bit boundary, stored from a
+    // branch -- confirming round 28 -> 8 us, but with 32 lanes crossing boundaries at different tokens the branch is
+    // taken by some lane in nearly every iteration and the hypothesis phases go from 105 to 160 us.)
     const bool half = p.hypotheses && g.sub_bits % 256u == 0 && p.mid.nsplit % 2u == 0;
     const uint32_t hstep = half ? 2u : 1u;
     // ---- phase hypotheses (see the header): seed entry[] with the states the true token sequence passes through
