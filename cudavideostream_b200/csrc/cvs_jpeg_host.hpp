@@ -134,6 +134,7 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
     set_std(1, 0, kStd_ac_lum_bits, kStd_ac_lum_vals, (int)sizeof kStd_ac_lum_vals);
     set_std(1, 1, kStd_ac_chrom_bits, kStd_ac_chrom_vals, (int)sizeof kStd_ac_chrom_vals);
     int width = 0, height = 0, ncomp = 0, hs[3] = {0, 0, 0}, vs[3] = {0, 0, 0}, tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    int cid[3] = {0, 0, 0};
     bool sof = false, sos = false;
     size_t i = 2;
     while (i + 4 <= n) {
@@ -189,6 +190,7 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
             if (ncomp != 3 && ncomp != 1) return kParseUnsupported;
             if (pl < 6 + 3 * (size_t)ncomp) return kParseNotJpeg;
             for (int c = 0; c < ncomp; c++) {
+                cid[c] = p[6 + 3 * c];
                 hs[c] = p[7 + 3 * c] >> 4;
                 vs[c] = p[7 + 3 * c] & 15;
                 tq[c] = p[8 + 3 * c];
@@ -203,6 +205,7 @@ inline ParseStatus parse(const uint8_t *d, size_t n, uint32_t sub_bits, Parsed *
         } else if (m == 0xDA) {
             if (!sof || pl < 1 || p[0] != ncomp || pl < 1 + 2 * (size_t)ncomp + 3) return sof ? kParseUnsupported : kParseNotJpeg;
             for (int c = 0; c < ncomp; c++) {
+                if (p[1 + 2 * c] != cid[c]) return kParseUnsupported; // scan components in another order than the frame's
                 td[c] = p[2 + 2 * c] >> 4;
                 ta[c] = p[2 + 2 * c] & 15;
                 if (td[c] > 3 || ta[c] > 3) return kParseNotJpeg;

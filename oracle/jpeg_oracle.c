@@ -37,7 +37,7 @@ typedef struct {
 
 typedef struct {
     int width, height, ncomp;
-    int hs[3], vs[3], tq[3], td[3], ta[3];
+    int hs[3], vs[3], tq[3], td[3], ta[3], cid[3];
     uint16_t q[4][64]; /* in zig-zag order as transmitted */
     int qpresent[4];
     huff_t dc[4], ac[4];
@@ -177,6 +177,7 @@ static int parse(const uint8_t *d, size_t n, jpg_t *j)
             j->ncomp = p[5];
             if ((j->ncomp != 3 && j->ncomp != 1) || pl < 6 + 3 * (size_t)j->ncomp) return -6;
             for (int c = 0; c < j->ncomp; c++) {
+                j->cid[c] = p[6 + 3 * c];
                 j->hs[c] = p[7 + 3 * c] >> 4;
                 j->vs[c] = p[7 + 3 * c] & 15;
                 j->tq[c] = p[8 + 3 * c];
@@ -191,6 +192,7 @@ static int parse(const uint8_t *d, size_t n, jpg_t *j)
         } else if (m == 0xDA) {
             if (!sof || pl < 1 || p[0] != j->ncomp || pl < 1 + 2 * (size_t)j->ncomp + 3) return -9;
             for (int c = 0; c < j->ncomp; c++) {
+                if (p[1 + 2 * c] != j->cid[c]) return -9; /* scan components in another order: not covered */
                 j->td[c] = p[2 + 2 * c] >> 4;
                 j->ta[c] = p[2 + 2 * c] & 15;
                 if (j->td[c] > 3 || j->ta[c] > 3) return -9;
