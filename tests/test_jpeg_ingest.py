@@ -262,6 +262,35 @@ def test_rejects_other_sizes_garbage_and_damaged_streams(cvs, monkeypatch):
             assert e.status == 1
 
 
+def test_damaged_headers_are_contained(cvs, oracle, monkeypatch):
+    """A frame whose header was damaged on the way (wrong Huffman / quantisation tables, other sampling factors, a
+    restart interval that is not there) either is refused or decodes to SOME picture: no crash, no hang, nothing written
+    outside the frame, and the library decodes the next good frame exactly (the CPU side of the same damage:
+    tests/test_jpeg_parse_fuzz.py)."""
+    monkeypatch.setenv("CVS_JPEG_DECODER", "own")
+    z = np.load(os.path.join(GOLDEN, "jpeg_cases.npz"))
+    rng = np.random.default_rng(23)
+    outcomes = {"decoded": 0, "refused": 0}
+    for name in ("q100_420_37x29", "q90_gray_123x77", "q85_444_161x97", "q95_420_rst4_256x144"):
+        good = z[name + "/jpg"].tobytes()
+        w, h = (int(v) for v in z[name + "/wh"])
+        sos = good.index(b"\xff\xda")
+        for trial in range(40):
+            m = bytearray(good)
+            for k in rng.integers(2, sos + 10, size=int(rng.integers(1, 4))):
+                m[k] = int(rng.integers(0, 256))
+            try:
+                g = _decode(cvs, bytes(m), w, h)  # checks the guard band behind the frame itself
+                assert g.size == 3 * w * h
+                outcomes["decoded"] += 1
+            except cvs.CVSError as e:
+                assert e.status == 1, f"{name} trial {trial}: status {e.status}"
+                outcomes["refused"] += 1
+        g = _decode(cvs, good, w, h)
+        assert np.array_equal(g, oracle.jpeg_decode_bgr(good).reshape(-1)), f"{name}: good frame after the damaged ones"
+    assert outcomes["decoded"] > 20 and outcomes["refused"] > 20, outcomes
+
+
 @pytest.mark.parametrize("name,dc_len,ac_len", [("q95_420_200x150", 11, 10), ("q90_gray_123x77", 10, 12), ("q92_420_1280x720", 16, 16)])
 def test_uniform_long_codes(cvs, oracle, monkeypatch, name, dc_len, ac_len):
     """Worst case for the decoder's look-up tables: every code dc_len / ac_len bits long (tests/util.transcode_huffman)."""
