@@ -282,6 +282,7 @@ StreamKernel pick_ws_kernel(int mode, bool hi, bool refreg)
 struct cvs_stream_s {
     int width = 0, height = 0, threshold = 20, mode = 0, noise_filter = 0, ksize = 3, device = 0;
     int max_sequence = 512;
+    bool fused_gray = false; // CVS_FUSED_GRAY=1: sequences in modes 5 / 7 keep gray + histogram inside the stream kernel (A/B timing)
     uint32_t N = 0, N16 = 0, nchunks = 0, npix = 0;
     size_t Npad = 0, P16 = 0;
     bool hi = false;
@@ -476,7 +477,10 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
 
     const int mode = h->mode;
     const bool binarize = (mode == 5 || mode == 7) && d_show;
-    const int kmode = d_show ? mode : 0; // without a display buffer only the payload is produced
+    // A sequence in a binarising mode computes the gray byte and the histograms in a kernel of its own in front of the
+    // plain stream kernel (k_gray_hist_seq: why, and what it measured); a single frame keeps the fused kernel.
+    const bool split_gray = binarize && nframes >= 2 && !h->fused_gray;
+    const int kmode = d_show && !split_gray ? mode : 0; // without a display buffer only the payload is produced
     const int piece_max = h->max_sequence < nframes ? h->max_sequence : nframes;
     const bool need_work = h->noise_filter || (txt.n && !frames_private);
     if (need_work) {
@@ -583,6 +587,14 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
             h->launches++;
         }
         if (binarize) CU_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)piece * 256 * sizeof(unsigned int), st));
+        if (split_gray) { // gray byte + histogram of the frames as the diff will see them (filtered, overlay blitted)
+            const size_t groups = ((size_t)h->N + cvs::kGroupBytes - 1) / cvs::kGroupBytes;
+            dim3 grid(grid_for((groups + cvs::kGrayHistGroupsPerThread - 1) / cvs::kGrayHistGroupsPerThread, 256, h->sms), piece);
+            if (mode == 5) cvs::k_gray_hist_seq<true><<<grid, 256, 0, st>>>(frames, fstride, h->N, h->d_gray1, h->P16, h->d_hist);
+            else cvs::k_gray_hist_seq<false><<<grid, 256, 0, st>>>(frames, fstride, h->N, h->d_gray1, h->P16, h->d_hist);
+            CU_TRY(cudaGetLastError());
+            h->launches++;
+        }
 
         cvs_status s = ensure_desc(h, (size_t)piece * nseg * (G + 1));
         if (s) return s;
@@ -616,9 +628,9 @@ cvs_status run_frames(cvs_handle h, const uint8_t *d_frames, size_t stride, int 
             p.cap = cap;
             p.show = d_show ? d_show + (size_t)done * show_stride : nullptr;
             p.show_stride = show_stride;
-            p.gray1 = binarize ? h->d_gray1 : nullptr;
+            p.gray1 = binarize && !split_gray ? h->d_gray1 : nullptr;
             p.gray_stride = h->P16;
-            p.hist = binarize ? h->d_hist : nullptr;
+            p.hist = binarize && !split_gray ? h->d_hist : nullptr;
             p.heat_lut = h->d_lut;
             p.desc = h->d_desc;
             p.epoch = h->epoch;
@@ -763,6 +775,7 @@ cvs_status cvs_create(const cvs_config *cfg, cvs_handle *out)
     }
     if (const char *tr = getenv("CVS_TRACE")) h->trace = atoi(tr) != 0;
     if (const char *co = getenv("CVS_COOP")) h->coop = atoi(co) != 0 ? 1 : 0;
+    if (const char *fg = getenv("CVS_FUSED_GRAY")) h->fused_gray = atoi(fg) != 0;
     if (const char *jd = getenv("CVS_JPEG_DECODER")) h->jpeg_decoder = !strcmp(jd, "own") ? 1 : (!strcmp(jd, "nvjpeg") ? 2 : 0);
     if (const char *hy = getenv("CVS_JPEG_HYPOTHESES")) h->jd[0].hypotheses = h->jd[1].hypotheses = h->jd[2].hypotheses = atoi(hy) != 0;
     if (const char *sb = getenv("CVS_JPEG_SUB_BITS")) { // subsequence length of the parallel Huffman decode (measurements)

@@ -434,6 +434,65 @@ __global__ void __launch_bounds__(256) k_filter(const uint8_t *__restrict__ prev
 }
 
 // ------------------------------------------------------------------------------------------------
+// Binarisation pass 1 of a SEQUENCE (modes 5, 7): gray byte of every pixel + one 256-bin histogram per frame
+// (server.cpp:96-106, tests/grayscale-weighted/cpu.cu:38-42), grid = (blocks per frame, frames).
+// In a sequence this runs as a kernel of its own in front of the plain diff+compact kernel instead of inside it:
+// k_stream_ws' front warps (4 per scheduler) are what the fused form waits for -- the exact weighted gray is ~15
+// instructions per pixel on them, 3.7 us per 1080p frame on top of the diff -- whereas here 64 warps per SM hide the
+// same arithmetic behind the frame's loads (one extra read of the frame, which HBM has room for; measured in
+// profiles/README.md).  Single frames (the drop-in call) keep the fused kernel: one launch less.
+//   hist: [nframes][256], zeroed by the caller; gray1: [nframes][gray_stride]
+// Lane L adds to histogram copy L mod kGrayHistCopies (copy-interleaved: the copies of a bin sit in different banks).
+// ------------------------------------------------------------------------------------------------
+#ifndef CVS_GRAY_HIST_COPIES
+#define CVS_GRAY_HIST_COPIES 1 // 4 / 8 / 16 copies measured 1-3 % slower (6.89 / 6.90 / 6.81 vs 6.72 us per frame, mode 5): not conflict-bound
+#endif
+constexpr int kGrayHistCopies = CVS_GRAY_HIST_COPIES;
+#ifndef CVS_GRAY_HIST_GROUPS
+#define CVS_GRAY_HIST_GROUPS 4
+#endif
+constexpr int kGrayHistGroupsPerThread = CVS_GRAY_HIST_GROUPS; // groups (16 pixels each) a thread walks: fewer histogram flushes per frame
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256) k_gray_hist_seq(const uint8_t *__restrict__ frames, size_t frame_stride, uint32_t nbytes,
+                                                        uint8_t *__restrict__ gray1, size_t gray_stride,
+                                                        unsigned int *__restrict__ hist)
+{
+    __shared__ uint32_t shist[256 * kGrayHistCopies];
+    for (uint32_t i = threadIdx.x; i < 256u * kGrayHistCopies; i += blockDim.x) shist[i] = 0;
+    __syncthreads();
+    const uint32_t t = blockIdx.y;
+    const uint8_t *cur = frames + (size_t)t * frame_stride;
+    uint8_t *gout = gray1 + (size_t)t * gray_stride;
+    const uint32_t copy = threadIdx.x & (kGrayHistCopies - 1);
+    const uint32_t ngroups = (nbytes + kGroupBytes - 1) / kGroupBytes;
+    for (uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x; gi < ngroups; gi += gridDim.x * blockDim.x) {
+        const uint32_t goff = gi * kGroupBytes;
+        const uint32_t nv = min(nbytes - goff, (uint32_t)kGroupBytes);
+        uint32_t c[kGroupWords], g4[4];
+        load_group(cur + goff, c, nv);
+        group_gray1<WEIGHTED>(c, g4);
+        const uint32_t npx = nv / 3u;
+        uint8_t *gd = gout + goff / 3u;
+        if (npx == (uint32_t)kGroupPixels) stg_stream(gd, make_uint4(g4[0], g4[1], g4[2], g4[3]));
+#pragma unroll
+        for (int px = 0; px < kGroupPixels; px++)
+            if ((uint32_t)px < npx) {
+                const uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                if (npx != (uint32_t)kGroupPixels) gd[px] = (uint8_t)gv;
+                atomicAdd(&shist[gv * kGrayHistCopies + copy], 1u); // server.cpp:103-106
+            }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t hv = 0;
+#pragma unroll
+        for (int k = 0; k < kGrayHistCopies; k++) hv += shist[i * kGrayHistCopies + k];
+        if (hv) atomicAdd(hist + (size_t)t * 256 + i, hv);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // client side of the wire format: frame[xs[i]] += diff[i]   (client/opencv.cpp:64-66)
 // xs is strictly ascending, so no two entries touch the same byte.
 // ------------------------------------------------------------------------------------------------

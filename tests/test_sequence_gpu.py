@@ -49,6 +49,36 @@ def test_sequence_matches_oracle(cvs, oracle, w, h, nframes, mode):
     s.close()
 
 
+@pytest.mark.parametrize("fused", ["0", "1"])
+@pytest.mark.parametrize("w,h,nframes,mode,noise", [(7, 5, 4, 5, False), (250, 130, 5, 7, False), (641, 359, 4, 5, True),
+                                                    (333, 77, 3, 7, True)])
+def test_binarising_sequences_split_and_fused(cvs, oracle, monkeypatch, fused, w, h, nframes, mode, noise):
+    """Sequences in modes 5 / 7 compute gray + histogram in k_gray_hist_seq in front of the plain stream kernel (default),
+    or inside the stream kernel (CVS_FUSED_GRAY=1, the form single frames use): same frames, same payload, either way
+    (server.cpp:96-135 behind the optional noise filter of kernels.cu:457-459)."""
+    import torch
+    monkeypatch.setenv("CVS_FUSED_GRAY", fused)
+    k = oracle.gaussian_kernel(3, 1.5)
+    cfg = dict(noise_filter=True, ksize=3, kweights=k) if noise else {}
+    ocfg = dict(noise_filter=1, K=3, k=k) if noise else {}
+    base, frames = random_sequence(w, h, nframes, 0.1, seed=3 * w + mode)
+    s, d_pos, d_xs, d_diff, d_show, cap, stride = _run_sequence(cvs, torch, w, h, base, frames, mode=mode, **cfg)
+    s.sequence_status()
+    oc = oracle.OracleCore(w, h, base, mode=mode, **ocfg)
+    pos = d_pos.cpu().numpy()
+    n = 3 * w * h
+    for t in range(nframes):
+        opos, oxs, odiff, oshow, _ = oc.exec_core(frames[t])
+        assert pos[t] == opos, f"frame {t}"
+        assert np.array_equal(d_xs[t * cap: t * cap + opos].cpu().numpy(), oxs), f"frame {t}"
+        assert np.array_equal(d_diff[t * cap: t * cap + opos].cpu().numpy(), odiff), f"frame {t}"
+        assert np.array_equal(d_show[t * stride: t * stride + n].cpu().numpy(), oshow), f"frame {t}: binarised frame"
+    assert np.array_equal(s.reference(), oc.reference())
+    # the split form is one launch more per piece (noise filter?, gray + histogram, stream kernel, threshold, binarize)
+    assert s.launch_count() == (4 if fused == "0" else 3) + (1 if noise else 0)
+    s.close()
+
+
 def test_sequence_capacity_overflow_is_reported(cvs):
     import torch
     w, h = 64, 48
