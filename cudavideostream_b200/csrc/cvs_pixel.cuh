@@ -26,7 +26,11 @@ enum Mode : int {
 // byte j (compile-time after unrolling) of a 12-word group
 __device__ __forceinline__ uint32_t gbyte(const uint32_t (&w)[kGroupWords], int j)
 {
+#ifdef CVS_GBYTE_SHIFT // (the shift-and-mask form: two instructions on the ALU pipe for bytes 1 and 2; A/B timing)
     return (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+#else
+    return __byte_perm(w[j >> 2], 0u, 0x4440u + (uint32_t)(j & 3)); // one PRMT
+#endif
 }
 // OR the 24-bit value u (B | G<<8 | R<<16) into pixel p of a zero-initialised group
 __device__ __forceinline__ void put_pixel(uint32_t (&o)[kGroupWords], int p, uint32_t u)
@@ -65,27 +69,63 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r)
     return WEIGHTED ? gray_weighted(b, g, r) : gray_avg(b, g, r);
 }
 
+// byte k of a word with ONE instruction (PRMT; the shift-and-mask form costs two on the same pipe)
+__device__ __forceinline__ uint32_t byte_of(uint32_t w, int k) { return __byte_perm(w, 0u, 0x4440u + (uint32_t)k); }
+
+// Four gray values (the four pixels of twelve frame bytes w0 w1 w2), packed into one word.
+// Weighted: the same values as gray_weighted(), arranged for the instruction scheduler -- the four pixels form ONE
+// basic block instead of four (a test-and-branch per pixel puts the pixels' multiply chains in series, and the warps
+// that run this inside k_stream_ws have few neighbours to hide them behind).  With M = 4,294,968 = ceil(2^32 / 1000)
+// the 64-bit product s * M holds s / 1000 in its upper word for every s <= 255,000 (the error 0.704 s stays below
+// 2^32 / 1000), and its lower word is below 1,000,000 exactly when s is a multiple of 1000 (remainder 0: <= 179,520;
+// remainder >= 1: >= 4,294,967).  Only then -- one pixel in a thousand -- the reference's double expression is evaluated.
+template <bool WEIGHTED>
+__device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    const uint32_t b[4] = {byte_of(w0, 0), byte_of(w0, 3), byte_of(w1, 2), byte_of(w2, 1)};
+    const uint32_t g[4] = {byte_of(w0, 1), byte_of(w1, 0), byte_of(w1, 3), byte_of(w2, 2)};
+    const uint32_t r[4] = {byte_of(w0, 2), byte_of(w1, 1), byte_of(w2, 0), byte_of(w2, 3)};
+    uint32_t q[4];
+    if (!WEIGHTED) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) q[i] = gray_avg(b[i], g[i], r[i]);
+    } else {
+        uint32_t s[4];
+        bool multiple = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            s[i] = 114u * b[i] + 587u * g[i] + 299u * r[i];
+            const uint64_t m = (uint64_t)s[i] * 4294968ull;
+            q[i] = (uint32_t)(m >> 32);
+            multiple |= (uint32_t)m < 1000000u;
+        }
+        if (multiple) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (s[i] == q[i] * 1000u) q[i] = gray_weighted(b[i], g[i], r[i]);
+        }
+    }
+    return __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+}
+
 // 16 gray values of a group, packed 4 per word
 template <bool WEIGHTED>
 __device__ __forceinline__ void group_gray1(const uint32_t (&c)[kGroupWords], uint32_t (&g)[4])
 {
 #pragma unroll
-    for (int i = 0; i < 4; i++) g[i] = 0;
-#pragma unroll
-    for (int p = 0; p < kGroupPixels; p++)
-        g[p >> 2] |= gray_of<WEIGHTED>(gbyte(c, 3 * p), gbyte(c, 3 * p + 1), gbyte(c, 3 * p + 2)) << (8 * (p & 3));
+    for (int i = 0; i < 4; i++) g[i] = gray4<WEIGHTED>(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
 }
 
-// gray replicated to the three channels
+// gray replicated to the three channels: pixels 4i..4i+3 = gray bytes (g0 g0 g0 g1 | g1 g1 g2 g2 | g2 g3 g3 g3)
 template <bool WEIGHTED>
 __device__ __forceinline__ void group_gray3(const uint32_t (&c)[kGroupWords], uint32_t (&o)[kGroupWords])
 {
 #pragma unroll
-    for (int k = 0; k < kGroupWords; k++) o[k] = 0;
-#pragma unroll
-    for (int p = 0; p < kGroupPixels; p++) {
-        uint32_t g = gray_of<WEIGHTED>(gbyte(c, 3 * p), gbyte(c, 3 * p + 1), gbyte(c, 3 * p + 2));
-        put_pixel(o, p, g * 0x010101u);
+    for (int i = 0; i < 4; i++) {
+        const uint32_t g = gray4<WEIGHTED>(c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+        o[3 * i] = __byte_perm(g, 0u, 0x1000);
+        o[3 * i + 1] = __byte_perm(g, 0u, 0x2211);
+        o[3 * i + 2] = __byte_perm(g, 0u, 0x3332);
     }
 }
 

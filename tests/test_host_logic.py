@@ -38,6 +38,17 @@ def test_weighted_gray_integer_shortcut_is_exact(oracle):
     assert np.all(fast[exact].astype(int) - want[exact].astype(int) <= 1)
 
 
+def test_weighted_gray_magic_multiply_is_exact():
+    # csrc/cvs_pixel.cuh gray4(): with M = 4,294,968 the 64-bit product s * M carries s / 1000 in its upper word and
+    # "s is a multiple of 1000" in its lower word (< 1,000,000), for every sum s = 114 B + 587 G + 299 R <= 255,000.
+    s = np.arange(0, 255001, dtype=np.uint64)
+    m = s * np.uint64(4294968)
+    hi, lo = (m >> np.uint64(32)).astype(np.int64), (m & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    assert np.array_equal(hi, s.astype(np.int64) // 1000)
+    assert np.array_equal(lo < 1000000, s.astype(np.int64) % 1000 == 0)
+    assert lo[s.astype(np.int64) % 1000 == 0].max() <= 179520 and lo[s.astype(np.int64) % 1000 != 0].min() >= 4294967
+
+
 def test_heat_table_is_monotone_blue_to_red(oracle):
     t = np.array([oracle.heat_pixel(d) for d in range(766)])
     r, g, b = t[:, 0], t[:, 1], t[:, 2]
