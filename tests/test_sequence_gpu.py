@@ -224,6 +224,32 @@ def test_standalone_filters(cvs, oracle):
     assert np.array_equal(d_o[:n].cpu().numpy(), oracle.binarize(np.repeat(g1, 3), thr))
 
 
+@pytest.mark.parametrize("th", [-1, 0, 1, 50, 127, 128, 129, 200, 254, 255, 300])
+def test_binarize_pass_at_every_kind_of_threshold(cvs, oracle, th):
+    """k_binarize_expand compares four gray bytes at once (carry-free byte compare, two forms for th < 128 and th >= 128);
+    clamp_lo = clamp_hi = th forces the frame's threshold: out = gray > th ? 255 : 0 per channel (server.cpp:129-135)."""
+    import torch
+    w, h = 253, 67  # a tail group (253 * 67 = 16,951 pixels = 1,059 groups + 7 pixels)
+    n, p = 3 * w * h, w * h
+    rng = np.random.default_rng(100 + th)
+    frame = rng.integers(0, 256, size=n, dtype=np.uint8)
+    frame[:3 * 256] = np.repeat(np.arange(256, dtype=np.uint8), 3)  # every gray value once (gray of (v, v, v) is v ...
+    d_f = torch.cat([torch.from_numpy(frame).cuda(), torch.zeros(64, dtype=torch.uint8, device="cuda")])
+    d_o = torch.full((n + 64,), 0x5A, dtype=torch.uint8, device="cuda")
+    d_g = torch.zeros(p + 64, dtype=torch.uint8, device="cuda")
+    d_ht = torch.zeros(257, dtype=torch.int32, device="cuda")
+    cvs.filters.binarize(d_f.data_ptr(), d_o.data_ptr(), d_g.data_ptr(), d_ht.data_ptr(), w, h, False, th, th,
+                         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    g1 = oracle.gray_avg1(frame, w, h)
+    assert np.array_equal(d_g[:p].cpu().numpy(), g1)
+    assert int(d_ht[256].item()) == th
+    want = np.where(np.repeat(g1, 3).astype(np.int64) > th, 255, 0).astype(np.uint8)
+    got = d_o.cpu().numpy()
+    assert np.array_equal(got[:n], want)
+    assert np.all(got[n:] == 0x5A)
+
+
 @pytest.mark.parametrize("w,h,mode", [(1919, 1079, 0), (641, 359, 1), (250, 130, 5), (7, 5, 3)])
 def test_no_write_outside_the_buffers(cvs, w, h, mode):
     # compute-sanitizer is closed on the pool, so out-of-bounds writes are caught with guard bands: every output
