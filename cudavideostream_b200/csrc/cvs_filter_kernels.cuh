@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(256) k_filter(const uint8_t *__restrict__ prev
 #pragma unroll
             for (int px = 0; px < kGroupPixels; px++)
                 if ((uint32_t)px < npx) {
-                    const uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                    const uint32_t gv = byte_of(g4[px >> 2], px & 3);
                     if (npx != (uint32_t)kGroupPixels) gd[px] = (uint8_t)gv;
                     if (hist) atomicAdd(&shist[gv], 1u);
                 }
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) k_gray_hist_seq(const uint8_t *__restrict
 #pragma unroll
         for (int px = 0; px < kGroupPixels; px++)
             if ((uint32_t)px < npx) {
-                const uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                const uint32_t gv = byte_of(g4[px >> 2], px & 3);
                 if (npx != (uint32_t)kGroupPixels) gd[px] = (uint8_t)gv;
                 atomicAdd(&shist[gv * kGrayHistCopies + copy], 1u); // server.cpp:103-106
             }

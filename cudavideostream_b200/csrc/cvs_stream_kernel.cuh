@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM) k_stream(const StreamP
 #pragma unroll
                         for (int px = 0; px < kGroupPixels; px++) {
                             if ((uint32_t)px < npx) {
-                                uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                                uint32_t gv = byte_of(g4[px >> 2], px & 3);
                                 if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
                                 atomicAdd(&shist[gv], 1u); // server.cpp:103-106
                             }

@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(kWsThreads, 1) k_stream_ws(const StreamParams 
 #pragma unroll
                         for (int px = 0; px < kGroupPixels; px++) {
                             if ((uint32_t)px < npx) {
-                                uint32_t gv = (g4[px >> 2] >> (8 * (px & 3))) & 0xffu;
+                                uint32_t gv = byte_of(g4[px >> 2], px & 3);
                                 if (npx != (uint32_t)kGroupPixels) gdst[px] = (uint8_t)gv;
 #ifndef CVS_EXP_NO_HIST // (timing experiment: the atomics are 0.68 of mode 5's 7.87 us per frame; the weighted gray of
                         //  32 pixels per thread, ~15 instructions each, is what mode 5 costs over mode 0)
