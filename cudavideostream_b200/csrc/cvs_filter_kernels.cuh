@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(256) k_conv_rows4(const uint8_t *__restrict__ 
 // 4 + 6*(K/2) bytes becomes a float once (PRMT into the mantissa of 2^23, one FADD) and stays in a K-row register
 // window, so an output costs K*K FFMA -- in the same row-major tap order as k_conv_rows4, hence the same bits.
 // NONNEG: all weights >= 0, so 0 <= acc < 2^23 and truncation is one FADD.RZ against 2^23 instead of F2I.
-constexpr int kConvRows = 8;
+#ifndef CVS_CONV_ROWS
+#define CVS_CONV_ROWS 8 // 12 / 16 / 24 rows per strip (fewer halo rows converted) measured the same: 6.67 / 6.66 / 6.73 vs 6.71 us per frame with the diff
+#endif
+constexpr int kConvRows = CVS_CONV_ROWS;
 
 __device__ __forceinline__ float byte_to_float(uint32_t word, int b) // b: compile-time byte index
 {
